@@ -1,0 +1,139 @@
+/* ffthom_b200.h — C ABI of libffthom_b200.so: the B200 (sm_100a) implementation of
+ * FFTHomPy's Fourier–Galerkin solve loop.
+ *
+ * The reference (vondrejc/FFTHomPy) is pure Python/NumPy and has no FFI; the entry
+ * points below are what a ctypes binding for its hot path binds.
+ * Each declaration cites the reference routine (path:line under the FFTHomPy tree)
+ * it replaces.
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative FH_ERR_* code; the message is
+ *    available from fh_last_error() (thread-local);
+ *  - all array arguments are caller-owned DEVICE pointers unless the name ends in
+ *    `_host`; the library never frees them and keeps none past the call except the
+ *    `A`/`work` pointers registered in an fh_ga operator;
+ *  - fields are C-contiguous, component-major: shape + N  (fp64) in real space and
+ *    shape + N_fft (complex128 = interleaved re,im doubles) in Fourier space, exactly
+ *    the layout of `Tensor.val` (ffthompy/tensors/objects.py:92-133);
+ *  - all work is enqueued on the stream given to fh_set_stream (default stream 0);
+ *    only functions that return scalars to the host synchronise.
+ */
+#ifndef FFTHOM_B200_H
+#define FFTHOM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FH_OK 0
+#define FH_ERR_CUDA -1
+#define FH_ERR_ARG -2
+#define FH_ERR_UNSUPPORTED -3
+#define FH_ERR_ALLOC -4
+
+/* fft_form codes (ffthompy/tensors/objects.py:47-66): 0 -> 0, 'r' -> 1, 'c' -> 2 */
+#define FH_FORM_0 0
+#define FH_FORM_R 1
+#define FH_FORM_C 2
+
+typedef struct fh_plan fh_plan; /* FFT plan of one grid N (twiddles, radix schedule) */
+typedef struct fh_ga fh_ga;     /* fused operator  x -> F^-1 G^ F (A x)               */
+
+/* Closed-form Green/projection multiplier (ffthompy/projections.py:9-112,114-267):
+ *   xi = 0               -> c0 * I
+ *   xi != 0, |k_i|<=band -> scale * (cI*I + cS*S + cH*v v^T + cL*Lambda + cW*(W+W^T))
+ *   otherwise            -> 0
+ * kind 0 (scalar problems, D = dim): only cI, cH (n (x) n) are used.
+ * kind 1 (elasticity, Mandel, D = dim(dim+1)/2).                                      */
+typedef struct fh_green {
+    int32_t kind;
+    int32_t dim;
+    int64_t N[3];
+    int64_t band[3];
+    double Y[3];
+    double c0, cI, cS, cH, cL, cW;
+    double scale;
+} fh_green;
+
+/* ---- lifecycle ------------------------------------------------------------------ */
+int fh_init(int device);
+int fh_set_stream(void* cuda_stream);
+int fh_sync(void);
+const char* fh_last_error(void);
+int fh_version(void);
+int fh_device_info(int* num_sms, int* smem_optin, int* l2_bytes);
+
+/* ---- FFT plan and transforms (ffthompy/tensors/fft.py:39-43; operators.py:14-58) -- */
+int fh_plan_create(fh_plan** plan, int dim, const int64_t* N);
+int fh_plan_destroy(fh_plan* plan);
+int fh_plan_factors(const fh_plan* plan, int axis, int* nfac, int* fac);
+/* numpy.fft.rfftn over the last `dim` axes, `batch` leading components, un-normalised */
+int fh_rfftn(const fh_plan* plan, const double* x, double* X, int64_t batch);
+/* x = scale * irfftn-sum (numpy.fft.irfftn == scale 1/prod(N)); work: spectrum-sized
+ * scratch keeping X intact, or NULL to transform X in place (destroying it)           */
+int fh_irfftn(const fh_plan* plan, const double* X, double* x, int64_t batch, double scale, double* work);
+
+/* ---- field algebra (ffthompy/tensors/objects.py:194-300,606-636) ------------------ */
+int fh_axpby(int64_t n, double a, const double* x, double b, const double* y /*or NULL*/, double* out);
+int fh_add_scalar(int64_t n, const double* x, double s, int is_complex, double* out);
+int fh_add_comp(int ncomp, int64_t n, double* x, const double* vals_host);
+int fh_dot(int64_t n, const double* x, const double* y, double* result_host);
+int fh_dot_rspec(const fh_plan* plan, int64_t batch, const double* x, const double* y, double* result_host);
+int fh_asum(int64_t n, const double* x, int is_complex, double* result_host);
+int fh_amax(int64_t n, const double* x, int is_complex, double* result_host);
+int fh_sum_comp(int ncomp, int64_t n, const double* x, double* result_host);
+int fh_poke(double* dst, int64_t offset, const double* vals_host, int64_t count);
+int fh_peek(const double* src, int64_t offset, double* vals_host, int64_t count);
+int fh_memset0(double* dst, int64_t count);
+int fh_copy(double* dst, const double* src, int64_t count);
+int fh_gather_comps(int64_t n, int ncomp, const int* perm_host, const double* in, double* out);
+
+/* ---- per-point contractions (tensors/objects.py:220-245,599-604; matvecs/objects.py:471-499) */
+int fh_mul21(int D, int64_t n, int K, const double* A, int a_complex, const double* x, int x_complex, double* y);
+int fh_hadamard(int64_t n, int nc, int ca, int cb, const double* a, int a_complex, const double* b, int b_complex,
+                double* out);
+int fh_contract_first(int64_t n, int d, int K, const double* a, const double* b, double* out);
+/* Gauss-Jordan inverse per voxel (ffthompy/trigpol.py:120-159) */
+int fh_inv_dxd(int D, int64_t n, const double* A, double* Ainv);
+
+/* ---- spectra: form changes, enlarge/decrease, shifts (tensors/objects.py:135-186,428-486;
+ *      trigpol.py:162-214) ----------------------------------------------------------- */
+int fh_spec_remap(int dim, const int64_t* N, int form_in, const int64_t* M, int form_out, int64_t batch, double scale,
+                  const double* in, double* out);
+int fh_roll(int dim, const int64_t* N, const int64_t* shift, int elem_doubles, int64_t batch, const double* in,
+            double* out);
+
+/* ---- Fourier differential operators (ffthompy/tensors/operators.py:227-312) ------- */
+int fh_grad(int dim, const int64_t* N, const double* Y, int form, int ncomp, const double* X, double* out);
+int fh_div(int dim, const int64_t* N, const double* Y, int form, int ncomp, const double* X, double* out);
+int fh_potential(int dim, const int64_t* N, const double* Y, int form, int ncomp, const double* X, double* out);
+
+/* ---- Green operators, unfused (projections.py; tensors/projection.py:33-70) ------- */
+int fh_green_apply(const fh_green* g, int form, int K, const double* X, double* out);
+int fh_green_materialize(const fh_green* g, int form, double* out);
+int fh_green4_materialize(int kind, int dim, const int64_t* N, const double* Y, int form, double* out);
+
+/* ---- fused operator  y = F^-1 G^ F (A x)  and Krylov loops -------------------------
+ * (Operator([[Operator([[FiN, G^, FN]]), A]]), tensors/operators.py:136-144;
+ *  CG / richardson, ffthompy/general/solver.py:63-139)
+ * a_layout: 0 = full D*D*n array (Tensor.val of the coefficient tensor)               */
+int64_t fh_ga_work_doubles(const fh_plan* plan, int D);
+int fh_ga_create(fh_ga** op, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
+                 double* work);
+int fh_ga_destroy(fh_ga* op);
+int fh_ga_apply(fh_ga* op, const double* x, double* y);
+/* vecs: 3*D*prod(N) doubles of scratch (r, p, Ap); x holds x0 on entry, the solution on exit;
+ * hist_host (optional, hist_cap entries) receives the residual norm after every iteration,
+ * entry 0 = initial residual                                                          */
+int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t maxiter, double* vecs, int64_t* kit_host,
+          double* norm_res_host, double* hist_host, int64_t hist_cap);
+/* vecs: 2*D*prod(N) doubles */
+int fh_richardson(fh_ga* op, const double* B, double* x, double alpha, double tol, int64_t maxiter, double* vecs,
+                  int64_t* kit_host, double* norm_res_host);
+/* kernels launched by this library since fh_init (for bench.py's gpu_launches) */
+int64_t fh_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
