@@ -1,0 +1,42 @@
+"""ffthompy_b200 — B200-native (sm_100a) implementation of FFTHomPy's Fourier-Galerkin solve
+loop behind FFTHomPy's own operator API.
+
+    from ffthompy_b200.tensors import Tensor, DFT, Operator, grad, div, potential
+    import ffthompy_b200.projections as proj
+    from ffthompy_b200.general.solver import linear_solver
+    from ffthompy_b200 import trigpol, matvecs
+
+mirror ffthompy.tensors / ffthompy.projections / ffthompy.general.solver / ffthompy.trigpol /
+ffthompy.matvecs (same names, arguments and error behaviour); `install()` splices them into an
+importable reference tree so that ffthompy.applications and the tutorials run on the GPU
+unmodified.  All arithmetic is hand-written CUDA behind the C ABI of
+libffthom_b200.so (include/ffthom_b200.h); there is no CPU fallback.
+"""
+import sys
+
+__version__ = '0.1.0'
+
+from .general.base import PrintControl, Timer  # noqa: F401,E402
+
+
+def install(reference_package='ffthompy'):
+    """Register this package's modules under the reference's module names, so that
+    `import ffthompy.applications` (and anything else in the reference tree that imports
+    ffthompy.tensors / .projections / .general.solver / .trigpol) binds the B200 objects.
+    Call before importing the reference's callers."""
+    import importlib
+    ref = importlib.import_module(reference_package)  # the reference tree must be importable
+    from . import tensors, projections, trigpol
+    from .tensors import objects, operators, projection
+    from .general import solver, solver_pp
+    mapping = {
+        'tensors': tensors, 'tensors.objects': objects, 'tensors.operators': operators,
+        'tensors.projection': projection, 'projections': projections,
+        'general.solver': solver, 'general.solver_pp': solver_pp, 'trigpol': trigpol,
+    }
+    for name, mod in mapping.items():
+        sys.modules[reference_package+'.'+name] = mod
+    ref.tensors = tensors
+    ref.projections = projections
+    ref.trigpol = trigpol
+    return mapping

@@ -47,7 +47,8 @@ _SIGNATURES = {
     'fh_add_scalar': (c_int, [c_i64, c_vp, c_dbl, c_int, c_vp]),
     'fh_add_comp': (c_int, [c_int, c_i64, c_vp, p_dbl]),
     'fh_dot': (c_int, [c_i64, c_vp, c_vp, p_dbl]),
-    'fh_dot_rspec': (c_int, [c_vp, c_i64, c_vp, c_vp, p_dbl]),
+    'fh_dot_rspec': (c_int, [c_vp, c_i64, c_int, c_vp, c_vp, p_dbl]),
+    'fh_convert': (c_int, [c_i64, c_vp, c_int, c_vp, c_int]),
     'fh_asum': (c_int, [c_i64, c_vp, c_int, p_dbl]),
     'fh_amax': (c_int, [c_i64, c_vp, c_int, p_dbl]),
     'fh_sum_comp': (c_int, [c_int, c_i64, c_vp, p_dbl]),
@@ -57,10 +58,10 @@ _SIGNATURES = {
     'fh_copy': (c_int, [c_vp, c_vp, c_i64]),
     'fh_gather_comps': (c_int, [c_i64, c_int, p_int, c_vp, c_vp]),
     'fh_mul21': (c_int, [c_int, c_i64, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
-    'fh_hadamard': (c_int, [c_i64, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
+    'fh_hadamard': (c_int, [c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     'fh_contract_first': (c_int, [c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'fh_inv_dxd': (c_int, [c_int, c_i64, c_vp, c_vp]),
-    'fh_spec_remap': (c_int, [c_int, p_i64, c_int, p_i64, c_int, c_i64, c_dbl, c_vp, c_vp]),
+    'fh_spec_remap': (c_int, [c_int, p_i64, c_int, p_i64, c_int, c_i64, c_dbl, c_int, c_vp, c_vp]),
     'fh_roll': (c_int, [c_int, p_i64, p_i64, c_int, c_i64, c_vp, c_vp]),
     'fh_grad': (c_int, [c_int, p_i64, p_dbl, c_int, c_int, c_vp, c_vp]),
     'fh_div': (c_int, [c_int, p_i64, p_dbl, c_int, c_int, c_vp, c_vp]),

@@ -138,9 +138,11 @@ static int launch_mid_green(fh_ga* op) {
 }
 
 // ------------------------------------------------------------------ operator object
+// sigma region rounded up to 128 B so that the spectrum behind it stays 16-byte aligned
+static int64_t sigma_doubles(const fh_plan* p, int D) { return ((int64_t)D * p->nreal + 15) / 16 * 16; }
 extern "C" int64_t fh_ga_work_doubles(const fh_plan* p, int D) {
     if (!p || D < 1) return 0;
-    return (int64_t)D * p->nreal + 2 * (int64_t)D * p->nspec;
+    return sigma_doubles(p, D) + 2 * (int64_t)D * p->nspec;
 }
 
 extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
@@ -165,7 +167,8 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     op->a_layout = a_layout;
     op->work = work;
     op->sigma = work;
-    op->spec = (cplx*)(work + (size_t)D * plan->nreal);
+    op->spec = (cplx*)(work + sigma_doubles(plan, D));
+    FH_REQUIRE(((uintptr_t)work & 15) == 0, "fh_ga_create: work must be 16-byte aligned");
     cudaError_t e = cudaMalloc((void**)&op->scal, sizeof(double) * (16 + GA_MAXPART));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&op->hist_pinned, sizeof(double) * 16);
     if (e != cudaSuccess) {

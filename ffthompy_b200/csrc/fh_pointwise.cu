@@ -159,8 +159,8 @@ extern "C" int fh_amax(int64_t n, const double* x, int is_complex, double* resul
 // Weighted half-spectrum product  sum_k w(k_last) Re(y conj x), w = 1 on the
 // k_last = 0 plane (and the Nyquist plane for even N_last), 2 elsewhere
 // (reference: scalar_product 'r' branch, tensors/objects.py:623-631, without 1/prod(N)^2).
-__global__ void k_dot_rspec(int64_t nrows, int nh, int nlast, const cplx* __restrict__ x, const cplx* __restrict__ y,
-                            double* __restrict__ part) {
+__global__ void k_dot_rspec(int64_t nrows, int nh, int nlast, int elem, const double* __restrict__ x,
+                            const double* __restrict__ y, double* __restrict__ part) {
     __shared__ double red[32];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t tot = nrows * nh;
@@ -168,12 +168,15 @@ __global__ void k_dot_rspec(int64_t nrows, int nh, int nlast, const cplx* __rest
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += stride) {
         const int k = (int)(i % nh);
         const double w = (k == 0 || 2 * k == nlast) ? 1.0 : 2.0;
-        acc += w * (y[i].x * x[i].x + y[i].y * x[i].y);
+        double v = y[i * elem] * x[i * elem];
+        if (elem == 2) v += y[i * 2 + 1] * x[i * 2 + 1];
+        acc += w * v;
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
-extern "C" int fh_dot_rspec(const fh_plan* p, int64_t batch, const double* x, const double* y, double* result) {
+extern "C" int fh_dot_rspec(const fh_plan* p, int64_t batch, int is_complex, const double* x, const double* y,
+                            double* result) {
     FH_REQUIRE(p && x && y && result && batch >= 0, "fh_dot_rspec: bad argument");
     int rc;
     if ((rc = ensure_scratch())) return rc;
@@ -184,9 +187,31 @@ extern "C" int fh_dot_rspec(const fh_plan* p, int64_t batch, const double* x, co
     }
     unsigned g = grid_for(nrows * p->nh, 8);
     if (g > FH_RED_MAX) g = FH_RED_MAX;
-    k_dot_rspec<<<g, FH_NT, 0, fh_stream()>>>(nrows, p->nh, p->N[p->dim - 1], (const cplx*)x, (const cplx*)y, g_red_dev);
+    k_dot_rspec<<<g, FH_NT, 0, fh_stream()>>>(nrows, p->nh, p->N[p->dim - 1], is_complex ? 2 : 1, x, y, g_red_dev);
     FH_LAUNCH_CHECK();
     return finish_reduction((int)g, 1, 0, result);
+}
+
+// real <-> complex copies: out = complex(in, 0) or out = Re(in)
+__global__ void k_convert(int64_t n, const double* __restrict__ in, int in_c, double* __restrict__ out, int out_c) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double re = in[i * (in_c ? 2 : 1)];
+        const double im = in_c ? in[i * 2 + 1] : 0.0;
+        if (out_c) {
+            out[i * 2] = re;
+            out[i * 2 + 1] = im;
+        } else {
+            out[i] = re;
+        }
+    }
+}
+extern "C" int fh_convert(int64_t n, const double* in, int in_complex, double* out, int out_complex) {
+    FH_REQUIRE(n >= 0 && in && out, "fh_convert: bad argument");
+    if (n == 0) return FH_OK;
+    k_convert<<<grid_for(n, 4), FH_NT, 0, fh_stream()>>>(n, in, in_complex, out, out_complex);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
 }
 
 // per-component sums: out[c] = sum_i x[c, i]   (Tensor.mean, tensors/objects.py:273-274)
@@ -360,14 +385,14 @@ extern "C" int fh_mul21(int D, int64_t n, int K, const double* A, int a_complex,
     return mul21_dispatch<false, false>(D, n, K, A, x, y);
 }
 
-// Hadamard product with broadcasting of x over `rep` leading components:
-// out[c, p] = a[c % ca, p] * b[c % cb, p]   (einsum '...,...->...' and the 'grad' multype
+// Hadamard product with component broadcasting:
+// out[c, p] = a[(c / adiv) % ca, p] * b[(c / bdiv) % cb, p]   (einsum '...,...->...' and the 'grad' multype
 // 'i...,...->i...', tensors/objects.py:235-238)
 template <bool AC, bool BC>
-__global__ void k_hadamard(int64_t n, int nc, int ca, int cb, const double* __restrict__ a,
+__global__ void k_hadamard(int64_t n, int nc, int adiv, int ca, int bdiv, int cb, const double* __restrict__ a,
                            const double* __restrict__ b, double* __restrict__ out) {
     const int c = blockIdx.y;
-    const size_t oa = (size_t)(c % ca) * n, ob = (size_t)(c % cb) * n, oo = (size_t)c * n;
+    const size_t oa = (size_t)((c / adiv) % ca) * n, ob = (size_t)((c / bdiv) % cb) * n, oo = (size_t)c * n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += stride) {
         const cplx u = AC ? ((const cplx*)a)[oa + p] : make_double2(a[oa + p], 0.0);
@@ -378,19 +403,20 @@ __global__ void k_hadamard(int64_t n, int nc, int ca, int cb, const double* __re
             out[oo + p] = u.x * v.x;
     }
 }
-extern "C" int fh_hadamard(int64_t n, int nc, int ca, int cb, const double* a, int a_complex, const double* b,
-                           int b_complex, double* out) {
-    FH_REQUIRE(n >= 0 && nc >= 1 && nc <= 65535 && ca >= 1 && cb >= 1 && a && b && out, "fh_hadamard: bad argument");
+extern "C" int fh_hadamard(int64_t n, int nc, int adiv, int ca, int bdiv, int cb, const double* a, int a_complex,
+                           const double* b, int b_complex, double* out) {
+    FH_REQUIRE(n >= 0 && nc >= 1 && nc <= 65535 && ca >= 1 && cb >= 1 && adiv >= 1 && bdiv >= 1 && a && b && out,
+               "fh_hadamard: bad argument");
     if (n == 0) return FH_OK;
     dim3 g(grid_for(n), nc);
     if (a_complex && b_complex)
-        k_hadamard<true, true><<<g, FH_NT, 0, fh_stream()>>>(n, nc, ca, cb, a, b, out);
+        k_hadamard<true, true><<<g, FH_NT, 0, fh_stream()>>>(n, nc, adiv, ca, bdiv, cb, a, b, out);
     else if (a_complex)
-        k_hadamard<true, false><<<g, FH_NT, 0, fh_stream()>>>(n, nc, ca, cb, a, b, out);
+        k_hadamard<true, false><<<g, FH_NT, 0, fh_stream()>>>(n, nc, adiv, ca, bdiv, cb, a, b, out);
     else if (b_complex)
-        k_hadamard<false, true><<<g, FH_NT, 0, fh_stream()>>>(n, nc, ca, cb, a, b, out);
+        k_hadamard<false, true><<<g, FH_NT, 0, fh_stream()>>>(n, nc, adiv, ca, bdiv, cb, a, b, out);
     else
-        k_hadamard<false, false><<<g, FH_NT, 0, fh_stream()>>>(n, nc, ca, cb, a, b, out);
+        k_hadamard<false, false><<<g, FH_NT, 0, fh_stream()>>>(n, nc, adiv, ca, bdiv, cb, a, b, out);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -493,6 +519,8 @@ struct RemapDesc {
     int dim;
     int N[3], M[3];
     int fin, fout;
+    int pure_pad;  // flags. bit 0: trigpol.enlarge semantics (no Nyquist splitting: bin -N/2 kept whole,
+                   // +N/2 empty); bit 1: take the Hermitian part (X(k)+conj X(-k))/2 of a full spectrum
     double scale;
 };
 
@@ -525,8 +553,12 @@ __global__ void k_spec_remap(RemapDesc d, int64_t nout, int64_t nin, int batch, 
                 const int ak = abs(k[a]);
                 if (2 * ak > N)
                     w = 0.0;
-                else if (2 * ak == N && d.M[a] > N)
-                    w *= 0.5;
+                else if (2 * ak == N && d.M[a] > N) {
+                    if (d.pure_pad & 1)
+                        w = (k[a] > 0) ? 0.0 : w;
+                    else
+                        w *= 0.5;
+                }
             }
         }
         if (w == 0.0) {
@@ -541,31 +573,42 @@ __global__ void k_spec_remap(RemapDesc d, int64_t nout, int64_t nin, int batch, 
             if (il < 0) il += N;
             if (il > N / 2) conj = true;
         }
-        int64_t src = 0;
+        int64_t src = 0, src2 = 0;  // src2: bin of -k (Hermitian-part option, full-spectrum sources only)
         for (int a = 0; a < dim; ++a) {
             const int N = d.N[a];
             int kk = conj ? -k[a] : k[a];
-            int ii;
+            int ii, i2;
             if (d.fin == 2) {
                 ii = kk + N / 2;  // centred storage (k = +N/2 of an even axis folds onto -N/2)
+                i2 = -kk + N / 2;
                 if (ii >= N) ii -= N;
                 if (ii < 0) ii += N;
+                if (i2 >= N) i2 -= N;
+                if (i2 < 0) i2 += N;
             } else {
                 ii = kk % N;
                 if (ii < 0) ii += N;
+                i2 = (-kk) % N;
+                if (i2 < 0) i2 += N;
             }
             src = src * si[a] + ii;
+            src2 = src2 * si[a] + i2;
         }
+        const bool herm = (d.pure_pad & 2) && d.fin != 1;
         for (int b = 0; b < batch; ++b) {
             cplx v = in[(size_t)b * nin + src];
             if (conj) v.y = -v.y;
+            if (herm) {  // (X(k) + conj X(-k)) / 2 : what ifftn(X).real sees
+                const cplx u = in[(size_t)b * nin + src2];
+                v = make_double2(0.5 * (v.x + u.x), 0.5 * (v.y - u.y));
+            }
             out[(size_t)b * nout + o] = make_double2(v.x * w, v.y * w);
         }
     }
 }
 
 extern "C" int fh_spec_remap(int dim, const int64_t* N, int form_in, const int64_t* M, int form_out, int64_t batch,
-                             double scale, const double* in, double* out) {
+                             double scale, int pure_pad, const double* in, double* out) {
     FH_REQUIRE(dim >= 1 && dim <= 3 && N && M && in && out && batch >= 0, "fh_spec_remap: bad argument");
     FH_REQUIRE(form_in >= 0 && form_in <= 2 && form_out >= 0 && form_out <= 2, "fh_spec_remap: bad fft form");
     RemapDesc d;
@@ -573,6 +616,7 @@ extern "C" int fh_spec_remap(int dim, const int64_t* N, int form_in, const int64
     d.fin = form_in;
     d.fout = form_out;
     d.scale = scale;
+    d.pure_pad = pure_pad;
     int64_t nout = 1, nin = 1;
     for (int a = 0; a < 3; ++a) {
         d.N[a] = a < dim ? (int)N[a] : 1;

@@ -78,7 +78,9 @@ int fh_axpby(int64_t n, double a, const double* x, double b, const double* y /*o
 int fh_add_scalar(int64_t n, const double* x, double s, int is_complex, double* out);
 int fh_add_comp(int ncomp, int64_t n, double* x, const double* vals_host);
 int fh_dot(int64_t n, const double* x, const double* y, double* result_host);
-int fh_dot_rspec(const fh_plan* plan, int64_t batch, const double* x, const double* y, double* result_host);
+int fh_dot_rspec(const fh_plan* plan, int64_t batch, int is_complex, const double* x, const double* y,
+                 double* result_host);
+int fh_convert(int64_t n, const double* in, int in_complex, double* out, int out_complex);
 int fh_asum(int64_t n, const double* x, int is_complex, double* result_host);
 int fh_amax(int64_t n, const double* x, int is_complex, double* result_host);
 int fh_sum_comp(int ncomp, int64_t n, const double* x, double* result_host);
@@ -90,16 +92,19 @@ int fh_gather_comps(int64_t n, int ncomp, const int* perm_host, const double* in
 
 /* ---- per-point contractions (tensors/objects.py:220-245,599-604; matvecs/objects.py:471-499) */
 int fh_mul21(int D, int64_t n, int K, const double* A, int a_complex, const double* x, int x_complex, double* y);
-int fh_hadamard(int64_t n, int nc, int ca, int cb, const double* a, int a_complex, const double* b, int b_complex,
-                double* out);
+/* out[c] = a[(c/adiv) % ca] * b[(c/bdiv) % cb], c < nc  (einsum '...,...->...' and 'i...,...->i...') */
+int fh_hadamard(int64_t n, int nc, int adiv, int ca, int bdiv, int cb, const double* a, int a_complex, const double* b,
+                int b_complex, double* out);
 int fh_contract_first(int64_t n, int d, int K, const double* a, const double* b, double* out);
 /* Gauss-Jordan inverse per voxel (ffthompy/trigpol.py:120-159) */
 int fh_inv_dxd(int D, int64_t n, const double* A, double* Ainv);
 
 /* ---- spectra: form changes, enlarge/decrease, shifts (tensors/objects.py:135-186,428-486;
  *      trigpol.py:162-214) ----------------------------------------------------------- */
+/* flags bit 0: trigpol.enlarge semantics (centred zero padding, no Nyquist splitting);
+ * flags bit 1: Hermitian part (X(k)+conj X(-k))/2 of a full-spectrum source (what ifftn(X).real sees) */
 int fh_spec_remap(int dim, const int64_t* N, int form_in, const int64_t* M, int form_out, int64_t batch, double scale,
-                  const double* in, double* out);
+                  int flags, const double* in, double* out);
 int fh_roll(int dim, const int64_t* N, const int64_t* shift, int elem_doubles, int64_t batch, const double* in,
             double* out);
 

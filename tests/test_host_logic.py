@@ -1,0 +1,110 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol declared in
+include/ffthom_b200.h, the host-side pattern matching of the solve-loop operator, the lazy
+Green-tensor algebra, and that compute calls fail loudly without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ffthompy_b200 import _lib as L
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, 'include', 'ffthom_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(fh_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = ctypes.CDLL(L.LIB_PATH)
+    declared = _header_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), 'libffthom_b200.so does not export %s' % name
+    assert sorted(L.EXPORTS) == declared, 'ctypes table and header disagree'
+
+
+def test_library_loads_and_reports_version():
+    lib = L.load()
+    assert lib.fh_version() >= 100
+    assert lib.fh_last_error() is not None
+
+
+def test_green_struct_layout_matches_header():
+    # int32 kind, dim; int64 N[3], band[3]; double Y[3]; 7 doubles
+    assert ctypes.sizeof(L.fh_green) == 8+24+24+24+7*8
+
+
+def _solve_operator(D=3, N=(6, 5, 4), elastic=False):
+    import ffthompy_b200.projections as proj
+    from ffthompy_b200.tensors import Tensor, DFT, Operator
+    N = np.array(N)
+    d = N.size
+    if elastic:
+        G = proj.elasticity(N, np.ones(d))
+        G = G[1]+G[2]
+        D = d*(d+1)//2
+    else:
+        G = proj.scalar(N, np.ones(d))[1]
+        D = d
+    A = Tensor(name='A', val=np.einsum('ij,...->ij...', np.eye(D), np.ones(tuple(N))), order=2, N=N, multype=21)
+    GN = Operator(name='G', mat=[[DFT(inverse=True, N=N), G, DFT(inverse=False, N=N)]])
+    return Operator(name='GA', mat=[[GN, A]]), A, G
+
+
+def test_operator_pattern_is_recognised():
+    from ffthompy_b200 import fused
+    for elastic in (False, True):
+        op, A, G = _solve_operator(elastic=elastic)
+        m = fused.match(op)
+        assert m is not None and m[0] is A and m[1] is G and m[2] == (6, 5, 4)
+    # a materialised multiplier (host touched .val) must NOT be fused
+    op, A, G = _solve_operator()
+    G.green = None
+    assert fused.match(op) is None
+
+
+def test_lazy_green_algebra_on_host():
+    import ffthompy_b200.projections as proj
+    N = np.array([6, 6, 6])
+    G0, G1h, G1s, G2h, G2s = proj.elasticity(N, np.ones(3))
+    G1 = G1h+G1s
+    assert G1.lazy and G1.green['coef']['cS'] == 1. and G1.green['coef']['cH'] == -1.
+    total = G0+G1h+G1s+G2h+G2s   # = identity inside the band
+    c = total.green['coef']
+    assert abs(c['cI']-1) < 1e-15 and abs(c['c0']-1) < 1e-15
+    assert all(abs(c[k]) < 1e-15 for k in ('cS', 'cH', 'cL', 'cW'))
+    assert tuple(G1.green['band']) == (2, 2, 2)
+    Gb = G1.enlarge(2*N-1)
+    assert tuple(Gb.N) == (11, 11, 11) and tuple(Gb.green['band']) == (2, 2, 2)
+    scale = 11.**3/6.**3
+    assert abs(Gb.green['coef']['cS']-scale) < 1e-12   # prod(Nbar)/prod(N)
+    MS = 0.25*G1h+2.*G1s
+    assert abs(MS.green['coef']['cH']-(0.25-4.)) < 1e-15
+    # reference quirk (tensors/objects.py:438): enlarge leaves its operand in the 'c' form, scaled by 1/prod(N)
+    assert G1.fft_form == 'c' and abs((-G1).green['coef']['cS']+1./216) < 1e-18
+
+
+def test_compute_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip('a GPU is visible')
+    from ffthompy_b200.tensors import Tensor
+    u = Tensor(name='u', val=np.ones((2, 4, 4)), order=1, N=(4, 4))
+    with pytest.raises(L.FhError):
+        u+u
+    with pytest.raises(L.FhError):
+        u.fourier()
+
+
+def test_no_product_module_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'ffthompy_b200')
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith('.py'):
+                src = open(os.path.join(dp, f)).read()
+                assert 'oracle' not in src.replace('no CPU oracle', ''), os.path.join(dp, f)
