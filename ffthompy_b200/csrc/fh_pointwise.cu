@@ -607,10 +607,62 @@ __global__ void k_spec_remap(RemapDesc d, int64_t nout, int64_t nin, int batch, 
     }
 }
 
+// trigpol.enlarge (trigpol.py:162-189) is positional: the block is copied to
+// [ceil((M-N)/2), ceil((M+N)/2)) of a zero array, whatever the parities of N and M.
+__global__ void k_pad_centred(RemapDesc d, int64_t nout, int64_t nin, int batch, const cplx* __restrict__ in,
+                              cplx* __restrict__ out) {
+    const int dim = d.dim;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nout; o += stride) {
+        int64_t r = o, src = 0, mul = 1;
+        bool inside = true;
+        for (int a = dim - 1; a >= 0; --a) {
+            const int j = (int)(r % d.M[a]);
+            r /= d.M[a];
+            const int ibeg = (d.M[a] - d.N[a] + 1) / 2;
+            const int i = j - ibeg;
+            inside = inside && i >= 0 && i < d.N[a];
+            src += (int64_t)i * mul;
+            mul *= d.N[a];
+        }
+        for (int b = 0; b < batch; ++b) {
+            cplx v = make_double2(0.0, 0.0);
+            if (inside) {
+                v = in[(size_t)b * nin + src];
+                v.x *= d.scale;
+                v.y *= d.scale;
+            }
+            out[(size_t)b * nout + o] = v;
+        }
+    }
+}
+
 extern "C" int fh_spec_remap(int dim, const int64_t* N, int form_in, const int64_t* M, int form_out, int64_t batch,
                              double scale, int pure_pad, const double* in, double* out) {
     FH_REQUIRE(dim >= 1 && dim <= 3 && N && M && in && out && batch >= 0, "fh_spec_remap: bad argument");
     FH_REQUIRE(form_in >= 0 && form_in <= 2 && form_out >= 0 && form_out <= 2, "fh_spec_remap: bad fft form");
+    if (pure_pad & 1) {
+        bool grow = true;
+        for (int a = 0; a < dim; ++a) grow = grow && M[a] >= N[a];
+        if (grow) {
+            FH_REQUIRE(form_in == 2 && form_out == 2, "fh_spec_remap: centred padding needs the 'c' form on both sides");
+            RemapDesc d;
+            d.dim = dim;
+            d.scale = scale;
+            int64_t nout = 1, nin = 1;
+            for (int a = 0; a < 3; ++a) {
+                d.N[a] = a < dim ? (int)N[a] : 1;
+                d.M[a] = a < dim ? (int)M[a] : 1;
+                nout *= d.M[a];
+                nin *= d.N[a];
+            }
+            if (batch == 0 || nout == 0) return FH_OK;
+            k_pad_centred<<<grid_for(nout), FH_NT, 0, fh_stream()>>>(d, nout, nin, (int)batch, (const cplx*)in,
+                                                                    (cplx*)out);
+            FH_LAUNCH_CHECK();
+            return FH_OK;
+        }
+    }
     RemapDesc d;
     d.dim = dim;
     d.fin = form_in;
@@ -737,8 +789,9 @@ __global__ void k_div(FreqDesc f, int64_t nf, int ncomp, const cplx* __restrict_
             for (int i = 0; i < f.dim; ++i) {
                 const double m = tp * ((double)k[i] / f.Y[i]);
                 const cplx v = X[((size_t)c * f.dim + i) * nf + o];
-                acc.x += -m * v.y;
-                acc.y += m * v.x;
+                // un-fused multiply/add: bit-identical to hD(hG(X)) evaluated through the multiplier tensors
+                acc.x = __dadd_rn(acc.x, __dmul_rn(-m, v.y));
+                acc.y = __dadd_rn(acc.y, __dmul_rn(m, v.x));
             }
             out[(size_t)c * nf + o] = acc;
         }
