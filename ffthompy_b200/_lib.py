@@ -73,6 +73,10 @@ _SIGNATURES = {
     'fh_ga_create': (c_int, [C.POINTER(c_vp), c_vp, c_int, c_vp, c_int, C.POINTER(fh_green), c_vp]),
     'fh_ga_destroy': (c_int, [c_vp]),
     'fh_ga_apply': (c_int, [c_vp, c_vp, c_vp]),
+    'fh_ga_config': (c_int, [c_vp, p_int, p_int, p_int]),
+    'fh_ga_stage': (c_int, [c_vp, c_int, c_vp, c_vp]),
+    'fh_cg_begin': (c_int, [c_vp, c_vp, c_vp, c_vp, p_dbl]),
+    'fh_cg_steps': (c_int, [c_vp, c_vp, c_vp, c_dbl, c_i64, p_i64, p_dbl, p_dbl]),
     'fh_cg': (c_int, [c_vp, c_vp, c_vp, c_dbl, c_i64, c_vp, p_i64, p_dbl, p_dbl, c_i64]),
     'fh_richardson': (c_int, [c_vp, c_vp, c_vp, c_dbl, c_dbl, c_i64, c_vp, p_i64, p_dbl]),
     'fh_launch_count': (c_i64, []),

@@ -1,0 +1,372 @@
+// fh_fast.cuh — register-resident two-pass FFT kernels for power-of-two axis lengths
+// (N = R1*R2 with radices <= 16: 64, 128, 256), the hot-path versions of the generic
+// shared-memory passes in fh_fft.cu.
+//
+// Design (fp64, HBM-bound): every thread owns one radix-R butterfly (<= 16 complex values in
+// registers).  Pass 1 loads its inputs straight from global memory (16 independent 16-byte
+// loads in flight per thread — the memory-level parallelism the generic kernels lacked),
+// exchanges through shared memory once, and pass 2 stores straight back to global memory in
+// natural order (Stockham autosort).  Strided axes move T adjacent lines per CTA so every
+// global access is a T*16-byte contiguous segment; the spectrum rows are padded to a multiple
+// of 8 complex numbers (128 B) so those segments are sector aligned.
+//
+//   pass 1 (radix R1, N/R1 = R2 butterflies per line):  a[j*R1 + q] = DFT_R1( x[j + r*R2] )
+//   pass 2 (radix R2, N/R2 = R1 butterflies per line):  X[j + q*R1] = DFT_R2( a[j + r*R1] * w_N^(r*j) )
+//
+// The inverse of the middle (Green) kernel runs the mirrored network (inverse of pass 2, then
+// inverse of pass 1), which consumes and produces exactly the rows each thread already owns,
+// so the whole forward-G^-inverse sequence is in place in shared memory.
+#pragma once
+#include "fh_fft.cuh"
+#include "fh_green.cuh"
+
+template <int N>
+struct Fac2;
+template <>
+struct Fac2<64> {
+    static constexpr int R1 = 8, R2 = 8;
+};
+template <>
+struct Fac2<128> {
+    static constexpr int R1 = 8, R2 = 16;
+};
+template <>
+struct Fac2<256> {
+    static constexpr int R1 = 16, R2 = 16;
+};
+
+static inline bool fh_fast_len(int n) { return n == 64 || n == 128 || n == 256; }
+
+template <int N>
+struct FastCfg {
+    static constexpr int R1 = Fac2<N>::R1, R2 = Fac2<N>::R2;
+    static constexpr int TPL = (R1 > R2) ? R1 : R2;  // threads per line
+};
+
+__device__ __forceinline__ cplx ldtw(const cplx* __restrict__ tw, int i, bool inv) {
+    cplx w = __ldg(&tw[i]);
+    if (inv) w.y = -w.y;
+    return w;
+}
+
+// ------------------------------------------------------------------ strided complex axis, in place
+// array [outer][N][inner]; inner % T == 0.  blockDim = T * TPL.
+template <int N, int T, bool INV>
+__global__ void __launch_bounds__(T* FastCfg<N>::TPL) k_c2c_fast(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                                  const cplx* __restrict__ tw, int64_t inner,
+                                                                  int ntile, double scale) {
+    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [N][T]
+    const int t = threadIdx.x % T, j = threadIdx.x / T;
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t base = o * N * inner + (int64_t)tile * T + t;
+    if (j < R2) {
+        cplx v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = in[base + (int64_t)(j + r * R2) * inner];
+        Bfly<R1, INV>::run(v);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) smc[(j * R1 + r) * T + t] = v[r];
+    }
+    __syncthreads();
+    if (j < R1) {
+        cplx v[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = smc[(j + r * R1) * T + t];
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ldtw(tw, r * j, INV));
+        Bfly<R2, INV>::run(v);
+#pragma unroll
+        for (int q = 0; q < R2; ++q)
+            out[base + (int64_t)(j + q * R1) * inner] = make_double2(v[q].x * scale, v[q].y * scale);
+    }
+}
+
+// ------------------------------------------------------------------ axis 0: forward, G^, inverse, in place
+// data [D][N][inner]; one CTA owns T consecutive inner positions of all D components.
+// blockDim = D * T * TPL.  nh = valid entries per spectrum row, pitch = padded row length.
+template <int N, int T, int KIND, int DIM>
+__global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) * T * FastCfg<N>::TPL)
+    k_mid_green_fast(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
+                     int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [D][N][T]
+    const int t = threadIdx.x % T;
+    const int c = (threadIdx.x / T) % D;
+    const int j = threadIdx.x / (T * D);
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    cplx* sc = smc + c * N * T;
+    cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+    // forward pass 1: global -> registers -> smem
+    if (j < R2) {
+        cplx v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = gp[(int64_t)(j + r * R2) * inner];
+        Bfly<R1, false>::run(v);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) sc[(j * R1 + r) * T + t] = v[r];
+    }
+    __syncthreads();
+    // forward pass 2, in place (reads and writes the rows j + r*R1 only)
+    if (j < R1) {
+        cplx v[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = sc[(j + r * R1) * T + t];
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ldtw(tw, r * j, false));
+        Bfly<R2, false>::run(v);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) sc[(j + q * R1) * T + t] = v[q];
+    }
+    __syncthreads();
+    // closed-form Green multiplier on every frequency of the tile
+    for (int it = threadIdx.x; it < N * T; it += blockDim.x) {
+        const int row = it / T, tt = it - row * T;
+        int k[3];
+        k[0] = fh_freq(row, N);
+        const int64_t ii = i0 + tt;
+        bool valid = true;
+        if (DIM == 3) {
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            k[1] = fh_freq(i1, g.N[1]);
+            k[2] = fh_freq(i2, g.N[2]);
+            valid = i2 < nh;
+        } else {
+            k[1] = fh_freq((int)ii, g.N[1]);
+            k[2] = 0;
+            valid = (int)ii < nh;
+        }
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = smc[(cc * N + row) * T + tt];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) smc[(cc * N + row) * T + tt] = e[cc];
+    }
+    __syncthreads();
+    // inverse of pass 2 (mirrored network), in place
+    if (j < R1) {
+        cplx v[R2];
+#pragma unroll
+        for (int q = 0; q < R2; ++q) v[q] = sc[(j + q * R1) * T + t];
+        Bfly<R2, true>::run(v);
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ldtw(tw, r * j, true));
+#pragma unroll
+        for (int r = 0; r < R2; ++r) sc[(j + r * R1) * T + t] = v[r];
+    }
+    __syncthreads();
+    // inverse of pass 1: smem -> registers -> global
+    if (j < R2) {
+        cplx v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) v[q] = sc[(j * R1 + q) * T + t];
+        Bfly<R1, true>::run(v);
+#pragma unroll
+        for (int r = 0; r < R1; ++r) gp[(int64_t)(j + r * R2) * inner] = v[r];
+    }
+}
+
+// ------------------------------------------------------------------ last axis, forward, fused with sigma = A p
+// Real fields [D][rows][N]; one CTA transforms TRW consecutive rows of all D components
+// (NL = D*TRW real lines, two per complex transform).  Shared memory holds the NP = NL/2 complex
+// lines as SoA (re plane, im plane), each line padded by one element per 16 (conflict-free
+// radix-16 scatter).  blockDim = NP * TPL.
+//   mode bit 0: p = r + beta*p first (the CG direction update, solver.py:132), beta = scal[3]
+//   A layout 0: full [D][D][n];  -1: no coefficient multiply (plain forward transform of x)
+__device__ __forceinline__ int pidx(int row) { return row + (row >> 4); }
+
+template <int N, int D, int TRW, int ALAY>
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+    k_fwd_last_fast(const double* __restrict__ A, double* __restrict__ p, const double* __restrict__ r,
+                    const double* __restrict__ scal, int pupdate, cplx* __restrict__ spec,
+                    const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
+    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
+    constexpr int NT = NP * TPL;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* smd = reinterpret_cast<double*>(fh_smem_raw);
+    double* zre = smd;              // [NP][NPAD]
+    double* zim = smd + NP * NPAD;  // [NP][NPAD]
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    const int64_t n = nrows * N;  // voxels per component
+    const double beta = pupdate ? scal[3] : 0.0;
+    // phase 0: sigma = A p on TRW x N voxels, two voxels per thread and step (16-byte accesses)
+    for (int v = threadIdx.x; v < TRW * (N / 2); v += NT) {
+        const int row = v / (N / 2), i2 = 2 * (v - row * (N / 2));
+        const int64_t gv = (row0 + row) * N + i2;
+        double2 pv[D];
+#pragma unroll
+        for (int jj = 0; jj < D; ++jj) {
+            double2 q = *reinterpret_cast<const double2*>(p + (size_t)jj * n + gv);
+            if (pupdate) {
+                const double2 rr = *reinterpret_cast<const double2*>(r + (size_t)jj * n + gv);
+                q = make_double2(rr.x + beta * q.x, rr.y + beta * q.y);
+                *reinterpret_cast<double2*>(p + (size_t)jj * n + gv) = q;
+            }
+            pv[jj] = q;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double2 s;
+            if (ALAY < 0) {
+                s = pv[i];
+            } else {
+                s = make_double2(0.0, 0.0);
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) {
+                    const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)i * D + jj) * n + gv);
+                    s.x += a.x * pv[jj].x;
+                    s.y += a.y * pv[jj].y;
+                }
+            }
+            const int L = i * TRW + row;
+            double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
+            dst[pidx(i2)] = s.x;
+            dst[pidx(i2 + 1)] = s.y;
+        }
+    }
+    __syncthreads();
+    const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
+    double* lre = zre + pr * NPAD;
+    double* lim = zim + pr * NPAD;
+    // pass 1 (rows j + r*R2 -> rows j*R1 + q): not in place, so read / barrier / write
+    {
+        cplx v[R1];
+        if (j < R2) {
+#pragma unroll
+            for (int rr = 0; rr < R1; ++rr) v[rr] = make_double2(lre[pidx(j + rr * R2)], lim[pidx(j + rr * R2)]);
+            Bfly<R1, false>::run(v);
+        }
+        __syncthreads();
+        if (j < R2) {
+#pragma unroll
+            for (int q = 0; q < R1; ++q) {
+                lre[pidx(j * R1 + q)] = v[q].x;
+                lim[pidx(j * R1 + q)] = v[q].y;
+            }
+        }
+    }
+    __syncthreads();
+    // pass 2, in place
+    if (j < R1) {
+        cplx v[R2];
+#pragma unroll
+        for (int rr = 0; rr < R2; ++rr) v[rr] = make_double2(lre[pidx(j + rr * R1)], lim[pidx(j + rr * R1)]);
+#pragma unroll
+        for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, false));
+        Bfly<R2, false>::run(v);
+#pragma unroll
+        for (int q = 0; q < R2; ++q) {
+            lre[pidx(j + q * R1)] = v[q].x;
+            lim[pidx(j + q * R1)] = v[q].y;
+        }
+    }
+    __syncthreads();
+    // separate the two real lines of every pair and store the half spectra (padding columns zeroed)
+    for (int it = threadIdx.x; it < NL * pitch; it += NT) {
+        const int L = it / pitch, k = it - L * pitch;
+        const int c = L / TRW, row = L - c * TRW;
+        cplx X = make_double2(0.0, 0.0);
+        if (k < nh) {
+            const double* qre = zre + (L >> 1) * NPAD;
+            const double* qim = zim + (L >> 1) * NPAD;
+            const int km = (k == 0) ? 0 : N - k;
+            const double ax_ = qre[pidx(k)], ay_ = qim[pidx(k)];
+            const double bx_ = qre[pidx(km)], by_ = qim[pidx(km)];
+            X = (L & 1) ? make_double2(0.5 * (ay_ + by_), -0.5 * (ax_ - bx_))
+                        : make_double2(0.5 * (ax_ + bx_), 0.5 * (ay_ - by_));
+        }
+        spec[((size_t)c * nrows + row0 + row) * pitch + k] = X;
+    }
+}
+
+// ------------------------------------------------------------------ last axis, inverse, fused with <p, y>
+// y[D][rows][N] = scale * C2R(spec); if pdot != NULL also part[blockIdx.x] = sum over the CTA's
+// voxels of pdot*y  (the p.Ap of CG, solver.py:126).
+template <int N, int D, int TRW>
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+    k_inv_last_fast(const cplx* __restrict__ spec, double* __restrict__ y, const double* __restrict__ pdot,
+                    double* __restrict__ part, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
+                    double scale) {
+    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
+    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
+    constexpr int NT = NP * TPL;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* smd = reinterpret_cast<double*>(fh_smem_raw);
+    __shared__ double red[32];
+    double* zre = smd;
+    double* zim = smd + NP * NPAD;
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    // phase 0: Z = X_a + i X_b on the full circle (Hermitian completion), natural order
+    for (int it = threadIdx.x; it < NP * nh; it += NT) {
+        const int pr = it / nh, k = it - pr * nh;
+        const int La = 2 * pr, Lb = 2 * pr + 1;
+        const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
+        cplx a = spec[((size_t)ca * nrows + row0 + ra) * pitch + k];
+        cplx b = spec[((size_t)cb * nrows + row0 + rb) * pitch + k];
+        if (k == 0 || 2 * k == N) {
+            a.y = 0.0;
+            b.y = 0.0;
+        }
+        double* qre = zre + pr * NPAD;
+        double* qim = zim + pr * NPAD;
+        qre[pidx(k)] = a.x - b.y;
+        qim[pidx(k)] = a.y + b.x;
+        if (k > 0 && 2 * k != N) {
+            qre[pidx(N - k)] = a.x + b.y;
+            qim[pidx(N - k)] = -a.y + b.x;
+        }
+    }
+    __syncthreads();
+    const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
+    double* lre = zre + pr * NPAD;
+    double* lim = zim + pr * NPAD;
+    // inverse of pass 2, in place
+    if (j < R1) {
+        cplx v[R2];
+#pragma unroll
+        for (int q = 0; q < R2; ++q) v[q] = make_double2(lre[pidx(j + q * R1)], lim[pidx(j + q * R1)]);
+        Bfly<R2, true>::run(v);
+#pragma unroll
+        for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, true));
+#pragma unroll
+        for (int rr = 0; rr < R2; ++rr) {
+            lre[pidx(j + rr * R1)] = v[rr].x;
+            lim[pidx(j + rr * R1)] = v[rr].y;
+        }
+    }
+    __syncthreads();
+    // inverse of pass 1: registers hold z[j + r*R2]; re -> line 2*pr, im -> line 2*pr+1
+    double acc = 0.0;
+    if (j < R2) {
+        cplx v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) v[q] = make_double2(lre[pidx(j * R1 + q)], lim[pidx(j * R1 + q)]);
+        Bfly<R1, true>::run(v);
+        const int La = 2 * pr, Lb = 2 * pr + 1;
+        const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
+        const size_t oa = ((size_t)ca * nrows + row0 + ra) * N, ob = ((size_t)cb * nrows + row0 + rb) * N;
+#pragma unroll
+        for (int rr = 0; rr < R1; ++rr) {
+            const int i2 = j + rr * R2;
+            const double ya = v[rr].x * scale, yb = v[rr].y * scale;
+            y[oa + i2] = ya;
+            y[ob + i2] = yb;
+            if (pdot) acc += pdot[oa + i2] * ya + pdot[ob + i2] * yb;
+        }
+    }
+    if (pdot) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    }
+}

@@ -154,7 +154,8 @@ extern "C" int fh_plan_factors(const fh_plan* p, int axis, int* nfac, int* fac) 
 template <bool INV>
 __global__ void __launch_bounds__(256) k_c2c_strided(const cplx* __restrict__ in, cplx* __restrict__ out, AxisDesc ax,
                                                      int64_t inner, int T, int ld, int ntiles, double scale) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* sm = reinterpret_cast<double*>(fh_smem_raw);
     const int n = ax.n;
     double* b0re = sm;
     double* b0im = sm + (size_t)n * ld;
@@ -184,8 +185,9 @@ __global__ void __launch_bounds__(256) k_c2c_strided(const cplx* __restrict__ in
 // Real -> half-spectrum along the contiguous last axis, two real lines per
 // complex transform (valid for even and odd n alike).
 __global__ void __launch_bounds__(256) k_r2c_last(const double* __restrict__ x, cplx* __restrict__ X, AxisDesc ax,
-                                                  int64_t nlines, int nh, int LP, int ld) {
-    extern __shared__ double sm[];
+                                                  int64_t nlines, int nh, int pitch, int LP, int ld) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* sm = reinterpret_cast<double*>(fh_smem_raw);
     const int n = ax.n;
     double* b0re = sm;
     double* b0im = sm + (size_t)n * ld;
@@ -217,15 +219,16 @@ __global__ void __launch_bounds__(256) k_r2c_last(const double* __restrict__ x, 
             r = make_double2(0.5 * (ay_ + by_), -0.5 * (ax_ - bx_));
         else
             r = make_double2(0.5 * (ax_ + bx_), 0.5 * (ay_ - by_));
-        X[(line0 + l) * nh + k] = r;
+        X[(line0 + l) * pitch + k] = r;
     }
 }
 
 // Half-spectrum -> real along the contiguous last axis (numpy irfft semantics:
 // the imaginary parts of the DC and, for even n, Nyquist bins are ignored).
 __global__ void __launch_bounds__(256) k_c2r_last(const cplx* __restrict__ X, double* __restrict__ x, AxisDesc ax,
-                                                  int64_t nlines, int nh, int LP, int ld, double scale) {
-    extern __shared__ double sm[];
+                                                  int64_t nlines, int nh, int pitch, int LP, int ld, double scale) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* sm = reinterpret_cast<double*>(fh_smem_raw);
     const int n = ax.n;
     double* b0re = sm;
     double* b0im = sm + (size_t)n * ld;
@@ -237,8 +240,8 @@ __global__ void __launch_bounds__(256) k_c2r_last(const cplx* __restrict__ X, do
     for (int idx = threadIdx.x; idx < npairs * nh; idx += blockDim.x) {
         const int pr = idx / nh, k = idx - pr * nh;
         const int64_t la = line0 + 2 * pr;
-        cplx a = X[la * nh + k];
-        cplx b = (2 * pr + 1 < nll) ? X[(la + 1) * nh + k] : make_double2(0.0, 0.0);
+        cplx a = X[la * pitch + k];
+        cplx b = (2 * pr + 1 < nll) ? X[(la + 1) * pitch + k] : make_double2(0.0, 0.0);
         if (k == 0 || 2 * k == n) {
             a.y = 0.0;
             b.y = 0.0;
@@ -303,7 +306,7 @@ int fh_launch_c2c_strided(const AxisDesc& ax, const cplx* in, cplx* out, int64_t
     return FH_OK;
 }
 
-int fh_launch_r2c_last(const fh_plan* p, const double* x, cplx* X, int64_t nlines) {
+int fh_launch_r2c_last(const fh_plan* p, const double* x, cplx* X, int64_t nlines, int pitch) {
     if (nlines <= 0) return FH_OK;
     const AxisDesc& ax = p->ax[p->dim - 1];
     const int LP = pick_lines(ax.n, 8);
@@ -313,12 +316,12 @@ int fh_launch_r2c_last(const fh_plan* p, const double* x, cplx* X, int64_t nline
     FH_REQUIRE(nblk < 2147483647LL, "r2c_last: grid too large");
     int rc;
     if ((rc = set_smem(k_r2c_last, smem))) return rc;
-    k_r2c_last<<<(unsigned)nblk, 256, smem, fh_stream()>>>(x, X, ax, nlines, p->nh, LP, ld);
+    k_r2c_last<<<(unsigned)nblk, 256, smem, fh_stream()>>>(x, X, ax, nlines, p->nh, pitch, LP, ld);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
 
-int fh_launch_c2r_last(const fh_plan* p, const cplx* X, double* x, int64_t nlines, double scale) {
+int fh_launch_c2r_last(const fh_plan* p, const cplx* X, double* x, int64_t nlines, int pitch, double scale) {
     if (nlines <= 0) return FH_OK;
     const AxisDesc& ax = p->ax[p->dim - 1];
     const int LP = pick_lines(ax.n, 8);
@@ -328,7 +331,7 @@ int fh_launch_c2r_last(const fh_plan* p, const cplx* X, double* x, int64_t nline
     FH_REQUIRE(nblk < 2147483647LL, "c2r_last: grid too large");
     int rc;
     if ((rc = set_smem(k_c2r_last, smem))) return rc;
-    k_c2r_last<<<(unsigned)nblk, 256, smem, fh_stream()>>>(X, x, ax, nlines, p->nh, LP, ld, scale);
+    k_c2r_last<<<(unsigned)nblk, 256, smem, fh_stream()>>>(X, x, ax, nlines, p->nh, pitch, LP, ld, scale);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -341,7 +344,7 @@ extern "C" int fh_rfftn(const fh_plan* p, const double* x, double* Xout, int64_t
     const int d = p->dim;
     const int64_t nlines = batch * (p->nreal / p->N[d - 1]);
     int rc;
-    if ((rc = fh_launch_r2c_last(p, x, X, nlines))) return rc;
+    if ((rc = fh_launch_r2c_last(p, x, X, nlines, p->nh))) return rc;
     if (d == 3) {
         if ((rc = fh_launch_c2c_strided(p->ax[1], X, X, batch * p->N[0], p->nh, false, 1.0))) return rc;
         if ((rc = fh_launch_c2c_strided(p->ax[0], X, X, batch, (int64_t)p->N[1] * p->nh, false, 1.0))) return rc;
@@ -370,5 +373,5 @@ extern "C" int fh_irfftn(const fh_plan* p, const double* Xin, double* x, int64_t
         if ((rc = fh_launch_c2c_strided(p->ax[0], src, W, batch, p->nh, true, 1.0))) return rc;
         src = W;
     }
-    return fh_launch_c2r_last(p, src, x, nlines, scale);
+    return fh_launch_c2r_last(p, src, x, nlines, p->nh, scale);
 }

@@ -4,15 +4,26 @@
 // Reference call path: applications.py:58-81 builds
 //   Afun = Operator([[ Operator([[FiN, G^, FN]]), A ]])      (tensors/operators.py:136-144)
 // and hands it to linear_solver('CG' | 'richardson')          (general/solver.py:63-139).
-// Here the whole operator is a fixed pipeline of axis passes; G^ is evaluated in
-// closed form between the forward and inverse transform of axis 0 (fh_green.cuh)
-// and is never materialised.
+// Here the operator is a fixed pipeline of five axis passes over a half spectrum whose rows
+// are padded to 128 B:
+//   S1  sigma = A p (fused with the CG direction update p = r + beta p) -> R2C along the last axis
+//   S2  C2C along axis 1                                   (3-D only)
+//   S3  C2C along axis 0, closed-form G^(xi), inverse C2C along axis 0   (fh_green.cuh; G^ is
+//       never materialised)
+//   S4  inverse C2C along axis 1                           (3-D only)
+//   S5  C2R along the last axis, scaled by 1/prod(N), fused with the partial sums of <p, Ap>
+// Power-of-two axis lengths (64, 128, 256) use the register-resident kernels of fh_fast.cuh,
+// any other length the generic shared-memory passes of fh_fft.cu.
 #include "fh_plan.cuh"
 #include "fh_green.cuh"
+#include "fh_fast.cuh"
 #include "../../include/ffthom_b200.h"
 #include <stdlib.h>
 
 int fh_fill_green(GreenDesc& g, const fh_green* in);
+
+#define GA_NT 256
+#define GA_MAXPART 16384
 
 struct fh_ga {
     const fh_plan* plan;
@@ -20,20 +31,30 @@ struct fh_ga {
     const double* A;
     int a_layout;
     GreenDesc g;
-    double* work;   // [D*nreal] sigma  |  [2*D*nspec] spectrum
-    double* sigma;  // = work
-    cplx* spec;     // = work + D*nreal
-    // device scalars for the Krylov loops
-    double* scal;  // [8]: rr, pAp, alpha, beta, ...
-    double* part;  // partial sums
-    double* hist_pinned;
-    int npart;
+    int pitch;       // padded spectrum row length (complex elements)
+    int64_t nrows;   // prod(N[:-1])
+    int64_t nspecp;  // nrows * pitch
+    double* work;
+    double* sigma;  // [D*nreal] (generic last-axis path only)
+    cplx* spec;     // [D][nrows][pitch]
+    // configuration
+    bool fast_last, fast_mid1, fast_mid0;
+    int mid_T, trw;
+    // device scalars / partial sums of the Krylov loops
+    double* scal;  // [16]: rr, pAp, alpha, beta, norm_res
+    double* part;  // [GA_MAXPART]
+    double* pinned;
+    // CG state (fh_cg_begin / fh_cg_steps)
+    int64_t kit;
+    int have_beta;
 };
 
-#define GA_NT 256
-#define GA_MAXPART 2048
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
 
-// ------------------------------------------------------------------ sigma = A x
+// ------------------------------------------------------------------ generic pieces
 template <int D>
 __global__ void k_apply_A(int64_t n, const double* __restrict__ A, const double* __restrict__ x,
                           double* __restrict__ y) {
@@ -52,14 +73,13 @@ __global__ void k_apply_A(int64_t n, const double* __restrict__ A, const double*
     }
 }
 
-// ------------------------------------------------------------------ axis 0: forward, G^, inverse
-// Array [D][n0][inner] (inner = N1*nh in 3-D, nh in 2-D).  One CTA owns T consecutive
-// `inner` positions of all D components, so G^ mixes components in shared memory.
+// Generic axis-0 pass with G^ (any length): array [D][n0][inner], ping-pong SoA buffers.
 template <int KIND, int DIM>
 __global__ void __launch_bounds__(GA_NT) k_mid_green(cplx* __restrict__ data, AxisDesc ax, GreenDesc g, int64_t inner,
-                                                     int T, int ld, int nh) {
+                                                     int T, int ld, int nh, int pitch) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* sm = reinterpret_cast<double*>(fh_smem_raw);
     const int n = ax.n;
     double* b0re = sm;
     double* b0im = sm + (size_t)n * ld;
@@ -86,18 +106,26 @@ __global__ void __launch_bounds__(GA_NT) k_mid_green(cplx* __restrict__ data, Ax
         int k[3];
         k[0] = fh_freq(row, n);
         const int64_t ii = i0 + t;
+        bool valid;
         if (DIM == 3) {
-            const int i1 = (int)(ii / nh), i2 = (int)(ii - (int64_t)i1 * nh);
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
             k[1] = fh_freq(i1, g.N[1]);
             k[2] = fh_freq(i2, g.N[2]);
+            valid = i2 < nh;
         } else {
             k[1] = fh_freq((int)ii, g.N[1]);
             k[2] = 0;
+            valid = (int)ii < nh;
         }
         cplx e[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) e[c] = make_double2(cre[row * ld + c * nl + t], cim[row * ld + c * nl + t]);
-        green_apply<KIND, DIM>(g, k, e);
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) e[c] = make_double2(0.0, 0.0);
+        }
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             cre[row * ld + c * nl + t] = e[c].x;
@@ -116,12 +144,11 @@ __global__ void __launch_bounds__(GA_NT) k_mid_green(cplx* __restrict__ data, Ax
 }
 
 template <int KIND, int DIM>
-static int launch_mid_green(fh_ga* op) {
+static int launch_mid_green_generic(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     const fh_plan* p = op->plan;
     const AxisDesc& ax = p->ax[0];
-    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * p->nh : p->nh;
-    // tile width: keep two CTAs per SM if possible
+    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
     int T = 8;
     while (T > 1 && fft_smem_bytes(ax.n, fft_ld(D * T)) > (size_t)113 * 1024) T >>= 1;
     while (T > 1 && fft_smem_bytes(ax.n, fft_ld(D * T)) > (size_t)fh_max_smem_optin()) T >>= 1;
@@ -132,17 +159,151 @@ static int launch_mid_green(fh_ga* op) {
     if (smem > 48 * 1024)
         FH_CUDA(cudaFuncSetAttribute(k_mid_green<KIND, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nblk = fh_ceil_div(inner, T);
-    k_mid_green<KIND, DIM><<<(unsigned)nblk, GA_NT, smem, fh_stream()>>>(op->spec, ax, op->g, inner, T, ld, p->nh);
+    k_mid_green<KIND, DIM><<<(unsigned)nblk, GA_NT, smem, fh_stream()>>>(op->spec, ax, op->g, inner, T, ld, p->nh,
+                                                                          op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
 
+// ------------------------------------------------------------------ fast-kernel launchers
+template <typename K>
+static int smem_attr(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return FH_OK;
+}
+
+template <int N, int T>
+static int launch_c2c_fast_NT(const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, double scale) {
+    const size_t smem = (size_t)N * T * sizeof(cplx);
+    const int ntile = (int)(inner / T);
+    const unsigned nblk = (unsigned)(outer * ntile);
+    const int nt = T * FastCfg<N>::TPL;
+    int rc;
+    if (inv) {
+        if ((rc = smem_attr(k_c2c_fast<N, T, true>, smem))) return rc;
+        k_c2c_fast<N, T, true><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, scale);
+    } else {
+        if ((rc = smem_attr(k_c2c_fast<N, T, false>, smem))) return rc;
+        k_c2c_fast<N, T, false><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, scale);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
+static int launch_c2c_fast(int N, const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv) {
+    switch (N) {
+        case 64: return launch_c2c_fast_NT<64, 8>(tw, data, outer, inner, inv, 1.0);
+        case 128: return launch_c2c_fast_NT<128, 8>(tw, data, outer, inner, inv, 1.0);
+        case 256: return launch_c2c_fast_NT<256, 8>(tw, data, outer, inner, inv, 1.0);
+    }
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no fast strided kernel for N=%d", N);
+}
+
+template <int N, int T, int KIND, int DIM>
+static int launch_mid_fast_NT(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const fh_plan* p = op->plan;
+    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const size_t smem = (size_t)D * N * T * sizeof(cplx);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_fast<N, T, KIND, DIM>, smem))) return rc;
+    k_mid_green_fast<N, T, KIND, DIM><<<(unsigned)(inner / T), D * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
+        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
+template <int KIND, int DIM>
+static int launch_mid_fast(fh_ga* op) {
+    const int N = op->plan->N[0];
+    const int T = op->mid_T;
+#define FH_MID_CASE(n, t) \
+    if (N == n && T == t) return launch_mid_fast_NT<n, t, KIND, DIM>(op);
+    FH_MID_CASE(64, 2)
+    FH_MID_CASE(64, 4)
+    FH_MID_CASE(128, 2)
+    FH_MID_CASE(128, 4)
+    FH_MID_CASE(256, 2)
+    FH_MID_CASE(256, 4)
+#undef FH_MID_CASE
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no fast Green kernel for N0=%d T=%d", N, T);
+}
+
+template <int N, int D, int TRW>
+static int launch_fwd_last_NT(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    constexpr int NP = D * TRW / 2, NPAD = N + N / 16;
+    const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
+    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const int nt = NP * FastCfg<N>::TPL;
+    const fh_plan* pl = op->plan;
+    const cplx* tw = pl->ax[pl->dim - 1].tw;
+    int rc;
+    if (withA) {
+        if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, 0>, smem))) return rc;
+        k_fwd_last_fast<N, D, TRW, 0><<<nblk, nt, smem, fh_stream()>>>(op->A, p, r, op->scal, pupdate, op->spec, tw,
+                                                                        op->nrows, pl->nh, op->pitch);
+    } else {
+        if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, -1>, smem))) return rc;
+        k_fwd_last_fast<N, D, TRW, -1><<<nblk, nt, smem, fh_stream()>>>(op->A, p, r, op->scal, pupdate, op->spec, tw,
+                                                                         op->nrows, pl->nh, op->pitch);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
+template <int N, int D, int TRW>
+static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npart) {
+    constexpr int NP = D * TRW / 2, NPAD = N + N / 16;
+    const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
+    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const int nt = NP * FastCfg<N>::TPL;
+    const fh_plan* pl = op->plan;
+    int rc;
+    if ((rc = smem_attr(k_inv_last_fast<N, D, TRW>, smem))) return rc;
+    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_fast<N, D, TRW><<<nblk, nt, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[pl->dim - 1].tw,
+                                                                op->nrows, pl->nh, op->pitch,
+                                                                1.0 / (double)pl->nreal);
+    FH_LAUNCH_CHECK();
+    if (npart) *npart = (int)nblk;
+    return FH_OK;
+}
+
+#define FH_LAST_DISPATCH(FN, ...)                                            \
+    do {                                                                     \
+        const int N_ = op->plan->N[op->plan->dim - 1];                       \
+        const int D_ = op->D;                                                \
+        if (D_ == 6) {                                                       \
+            if (N_ == 64) return FN<64, 6, 4>(__VA_ARGS__);                  \
+            if (N_ == 128) return FN<128, 6, 4>(__VA_ARGS__);                \
+            if (N_ == 256) return FN<256, 6, 4>(__VA_ARGS__);                \
+        } else if (D_ == 3) {                                                \
+            if (N_ == 64) return FN<64, 3, 8>(__VA_ARGS__);                  \
+            if (N_ == 128) return FN<128, 3, 8>(__VA_ARGS__);                \
+            if (N_ == 256) return FN<256, 3, 8>(__VA_ARGS__);                \
+        } else if (D_ == 2) {                                                \
+            if (N_ == 64) return FN<64, 2, 8>(__VA_ARGS__);                  \
+            if (N_ == 128) return FN<128, 2, 8>(__VA_ARGS__);                \
+            if (N_ == 256) return FN<256, 2, 8>(__VA_ARGS__);                \
+        }                                                                    \
+        return fh_set_error(FH_ERR_UNSUPPORTED, "no fast last-axis kernel"); \
+    } while (0)
+
+static int launch_fwd_last_fast(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    FH_LAST_DISPATCH(launch_fwd_last_NT, op, p, r, pupdate, withA);
+}
+static int launch_inv_last_fast(fh_ga* op, double* y, const double* pdot, int* npart) {
+    FH_LAST_DISPATCH(launch_inv_last_NT, op, y, pdot, npart);
+}
+static int trw_for(int D) { return D == 6 ? 4 : 8; }
+
 // ------------------------------------------------------------------ operator object
-// sigma region rounded up to 128 B so that the spectrum behind it stays 16-byte aligned
 static int64_t sigma_doubles(const fh_plan* p, int D) { return ((int64_t)D * p->nreal + 15) / 16 * 16; }
+static int pitch_for(const fh_plan* p) { return (p->nh + 7) / 8 * 8; }
+
 extern "C" int64_t fh_ga_work_doubles(const fh_plan* p, int D) {
     if (!p || D < 1) return 0;
-    return sigma_doubles(p, D) + 2 * (int64_t)D * p->nspec;
+    return sigma_doubles(p, D) + 2 * (int64_t)D * (p->nreal / p->N[p->dim - 1]) * pitch_for(p);
 }
 
 extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
@@ -150,6 +311,7 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     FH_REQUIRE(out && plan && A && g && work, "fh_ga_create: null argument");
     FH_REQUIRE(plan->dim == 2 || plan->dim == 3, "fh_ga_create: dim must be 2 or 3");
     FH_REQUIRE(a_layout == 0, "fh_ga_create: unsupported coefficient layout %d", a_layout);
+    FH_REQUIRE(((uintptr_t)work & 15) == 0 && ((uintptr_t)A & 15) == 0, "fh_ga_create: buffers must be 16-byte aligned");
     const int Dexp = (g->kind == FH_GREEN_SCALAR) ? plan->dim : plan->dim * (plan->dim + 1) / 2;
     FH_REQUIRE(D == Dexp, "fh_ga_create: D=%d does not match Green kind %d in dim %d", D, g->kind, plan->dim);
     for (int a = 0; a < plan->dim; ++a)
@@ -165,12 +327,26 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     op->D = D;
     op->A = A;
     op->a_layout = a_layout;
+    op->pitch = pitch_for(plan);
+    op->nrows = plan->nreal / plan->N[plan->dim - 1];
+    op->nspecp = op->nrows * op->pitch;
     op->work = work;
     op->sigma = work;
     op->spec = (cplx*)(work + sigma_doubles(plan, D));
-    FH_REQUIRE(((uintptr_t)work & 15) == 0, "fh_ga_create: work must be 16-byte aligned");
+    const int use_fast = env_int("FH_FAST", 1);
+    const int d = plan->dim;
+    op->trw = trw_for(D);
+    op->fast_last = use_fast && fh_fast_len(plan->N[d - 1]) && (op->nrows % op->trw == 0);
+    op->fast_mid1 = use_fast && d == 3 && fh_fast_len(plan->N[1]);
+    op->fast_mid0 = use_fast && fh_fast_len(plan->N[0]);
+    op->mid_T = env_int("FH_MID_T", 4);
+    if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
+    if ((size_t)D * plan->N[0] * op->mid_T * sizeof(cplx) > (size_t)fh_max_smem_optin()) op->mid_T = 2;
     cudaError_t e = cudaMalloc((void**)&op->scal, sizeof(double) * (16 + GA_MAXPART));
-    if (e == cudaSuccess) e = cudaMallocHost((void**)&op->hist_pinned, sizeof(double) * 16);
+    if (e == cudaSuccess) e = cudaMallocHost((void**)&op->pinned, sizeof(double) * 16);
+    if (e == cudaSuccess) e = cudaMemset(op->scal, 0, sizeof(double) * (16 + GA_MAXPART));
+    // padding columns of the spectrum rows are never read as data; zero them once for determinism
+    if (e == cudaSuccess) e = cudaMemset(op->spec, 0, sizeof(cplx) * D * op->nspecp);
     if (e != cudaSuccess) {
         free(op);
         return fh_set_error(FH_ERR_CUDA, "fh_ga_create: %s", cudaGetErrorString(e));
@@ -183,8 +359,17 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
 extern "C" int fh_ga_destroy(fh_ga* op) {
     if (!op) return FH_OK;
     cudaFree(op->scal);
-    cudaFreeHost(op->hist_pinned);
+    cudaFreeHost(op->pinned);
     free(op);
+    return FH_OK;
+}
+
+// which kernels an operator uses: bit0 fast last axis, bit1 fast axis 1, bit2 fast axis 0
+extern "C" int fh_ga_config(const fh_ga* op, int* flags, int* pitch, int* mid_T) {
+    FH_REQUIRE(op, "fh_ga_config: null argument");
+    if (flags) *flags = (op->fast_last ? 1 : 0) | (op->fast_mid1 ? 2 : 0) | (op->fast_mid0 ? 4 : 0);
+    if (pitch) *pitch = op->pitch;
+    if (mid_T) *mid_T = op->mid_T;
     return FH_OK;
 }
 
@@ -195,34 +380,6 @@ static unsigned ga_grid(int64_t n) {
     if (b > GA_MAXPART) b = GA_MAXPART;
     if (b < 1) b = 1;
     return (unsigned)b;
-}
-
-extern "C" int fh_ga_apply(fh_ga* op, const double* x, double* y) {
-    FH_REQUIRE(op && x && y, "fh_ga_apply: null argument");
-    const fh_plan* p = op->plan;
-    const int D = op->D;
-    const int64_t n = p->nreal;
-    const unsigned g = ga_grid(n);
-    switch (D) {
-        case 2: k_apply_A<2><<<g, GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
-        case 3: k_apply_A<3><<<g, GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
-        case 6: k_apply_A<6><<<g, GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
-        default: return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_apply: D=%d", D);
-    }
-    FH_LAUNCH_CHECK();
-    int rc;
-    const int64_t nlines = (int64_t)D * (p->nreal / p->N[p->dim - 1]);
-    if ((rc = fh_launch_r2c_last(p, op->sigma, op->spec, nlines))) return rc;
-    if (p->dim == 3)
-        if ((rc = fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], p->nh, false, 1.0))) return rc;
-    if (op->g.kind == FH_GREEN_SCALAR)
-        rc = (p->dim == 3) ? launch_mid_green<FH_GREEN_SCALAR, 3>(op) : launch_mid_green<FH_GREEN_SCALAR, 2>(op);
-    else
-        rc = (p->dim == 3) ? launch_mid_green<FH_GREEN_ELASTIC, 3>(op) : launch_mid_green<FH_GREEN_ELASTIC, 2>(op);
-    if (rc) return rc;
-    if (p->dim == 3)
-        if ((rc = fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], p->nh, true, 1.0))) return rc;
-    return fh_launch_c2r_last(p, op->spec, y, nlines, 1.0 / (double)p->nreal);
 }
 
 // ------------------------------------------------------------------ Krylov kernels
@@ -279,10 +436,28 @@ __global__ void k_cg_scal(int np, const double* __restrict__ part, double* __res
     }
 }
 
-// x += alpha p ; r -= alpha Ap ; partial r.r   (solver.py:127-129)
-__global__ void k_cg_update(int64_t n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
-                            const double* __restrict__ Ap, const double* __restrict__ scal,
+// x += alpha p ; r -= alpha Ap ; partial r.r   (solver.py:127-129); 16-byte accesses
+__global__ void k_cg_update(int64_t n2, double2* __restrict__ x, double2* __restrict__ r, const double2* __restrict__ p,
+                            const double2* __restrict__ Ap, const double* __restrict__ scal,
                             double* __restrict__ part) {
+    __shared__ double red[32];
+    const double alpha = scal[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 xv = x[i], pv = p[i], rv = r[i], av = Ap[i];
+        x[i] = make_double2(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
+        const double2 v = make_double2(rv.x - alpha * av.x, rv.y - alpha * av.y);
+        r[i] = v;
+        acc += v.x * v.x;
+        acc += v.y * v.y;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+__global__ void k_cg_update1(int64_t n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                             const double* __restrict__ Ap, const double* __restrict__ scal,
+                             double* __restrict__ part) {
     __shared__ double red[32];
     const double alpha = scal[2];
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -320,48 +495,167 @@ __global__ void k_rich_update(int64_t n, double* __restrict__ x, const double* _
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
-static int read_norm(fh_ga* op, double* out) {
-    FH_CUDA(cudaMemcpyAsync(op->hist_pinned, op->scal + 4, sizeof(double), cudaMemcpyDeviceToHost, fh_stream()));
-    FH_CUDA(cudaStreamSynchronize(fh_stream()));
-    *out = op->hist_pinned[0];
+// ------------------------------------------------------------------ the pipeline, stage by stage
+// stage 1..5 as in the header comment.  `x` is the operand (for the CG loop: p, updated in place
+// from r when pupdate != 0).  After stage 5 with dot != 0, op->part[0..*npart) holds the partial
+// sums of <x, y>.
+static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdate, double* y, int dot, int* npart) {
+    const fh_plan* p = op->plan;
+    const int D = op->D, d = p->dim;
+    const int64_t n = p->nreal;
+    const int64_t nlines = (int64_t)D * op->nrows;
+    int rc;
+    switch (stage) {
+        case 1:
+            if (op->fast_last) return launch_fwd_last_fast(op, x, r, pupdate, true);
+            if (pupdate) {
+                k_cg_pupdate<<<ga_grid(D * n), GA_NT, 0, fh_stream()>>>(D * n, x, r, op->scal);
+                FH_LAUNCH_CHECK();
+            }
+            switch (D) {
+                case 2: k_apply_A<2><<<ga_grid(n), GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
+                case 3: k_apply_A<3><<<ga_grid(n), GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
+                case 6: k_apply_A<6><<<ga_grid(n), GA_NT, 0, fh_stream()>>>(n, op->A, x, op->sigma); break;
+                default: return fh_set_error(FH_ERR_UNSUPPORTED, "fused operator: D=%d", D);
+            }
+            FH_LAUNCH_CHECK();
+            return fh_launch_r2c_last(p, op->sigma, op->spec, nlines, op->pitch);
+        case 2:
+            if (d != 3) return FH_OK;
+            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * p->N[0], op->pitch, false);
+            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], op->pitch, false, 1.0);
+        case 3:
+            if (op->fast_mid0) {
+                if (op->g.kind == FH_GREEN_SCALAR)
+                    return (d == 3) ? launch_mid_fast<FH_GREEN_SCALAR, 3>(op) : launch_mid_fast<FH_GREEN_SCALAR, 2>(op);
+                return (d == 3) ? launch_mid_fast<FH_GREEN_ELASTIC, 3>(op) : launch_mid_fast<FH_GREEN_ELASTIC, 2>(op);
+            }
+            if (op->g.kind == FH_GREEN_SCALAR)
+                return (d == 3) ? launch_mid_green_generic<FH_GREEN_SCALAR, 3>(op)
+                                : launch_mid_green_generic<FH_GREEN_SCALAR, 2>(op);
+            return (d == 3) ? launch_mid_green_generic<FH_GREEN_ELASTIC, 3>(op)
+                            : launch_mid_green_generic<FH_GREEN_ELASTIC, 2>(op);
+        case 4:
+            if (d != 3) return FH_OK;
+            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * p->N[0], op->pitch, true);
+            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], op->pitch, true, 1.0);
+        case 5:
+            if (op->fast_last) return launch_inv_last_fast(op, y, dot ? x : NULL, npart);
+            if ((rc = fh_launch_c2r_last(p, op->spec, y, nlines, op->pitch, 1.0 / (double)n))) return rc;
+            if (dot) {
+                const unsigned g = ga_grid(D * n);
+                k_dot_part<<<g, GA_NT, 0, fh_stream()>>>(D * n, x, y, op->part);
+                FH_LAUNCH_CHECK();
+                if (npart) *npart = (int)g;
+            }
+            return FH_OK;
+    }
+    return fh_set_error(FH_ERR_ARG, "fused operator: bad stage %d", stage);
+}
+
+static int ga_matvec(fh_ga* op, double* x, const double* r, int pupdate, double* y, int dot, int* npart) {
+    int rc;
+    for (int s = 1; s <= 5; ++s)
+        if ((rc = ga_stage(op, s, x, r, pupdate, y, dot, npart))) return rc;
     return FH_OK;
 }
 
-extern "C" int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t maxiter, double* vecs,
-                     int64_t* kit_host, double* norm_res_host, double* hist_host, int64_t hist_cap) {
-    FH_REQUIRE(op && B && x && vecs && kit_host && norm_res_host, "fh_cg: null argument");
+extern "C" int fh_ga_apply(fh_ga* op, const double* x, double* y) {
+    FH_REQUIRE(op && x && y, "fh_ga_apply: null argument");
+    return ga_matvec(op, (double*)x, NULL, 0, y, 0, NULL);
+}
+
+// Run ONE stage of the pipeline (profiling / roofline accounting in bench.py); the spectrum
+// workspace carries the state between stages.
+extern "C" int fh_ga_stage(fh_ga* op, int stage, const double* x, double* y) {
+    FH_REQUIRE(op && x && y, "fh_ga_stage: null argument");
+    int np = 0;
+    return ga_stage(op, stage, (double*)x, NULL, 0, y, 1, &np);
+}
+
+static int read_norm(fh_ga* op, double* out) {
+    FH_CUDA(cudaMemcpyAsync(op->pinned, op->scal + 4, sizeof(double), cudaMemcpyDeviceToHost, fh_stream()));
+    FH_CUDA(cudaStreamSynchronize(fh_stream()));
+    *out = op->pinned[0];
+    return FH_OK;
+}
+
+// vecs = [r | p | Ap], each D*prod(N) doubles.
+// fh_cg_begin: Ax = Afun(x0); R = B - Ax; P = R; rr = <R,R>      (solver.py:113-120)
+extern "C" int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, double* norm_res_host) {
+    FH_REQUIRE(op && B && x && vecs && norm_res_host, "fh_cg_begin: null argument");
     const int64_t n = (int64_t)op->D * op->plan->nreal;
     const double inv = 1.0 / (double)op->plan->nreal;
     double* r = vecs;
     double* p = vecs + n;
     double* Ap = vecs + 2 * n;
     const unsigned g = ga_grid(n);
+    int rc;
+    if ((rc = ga_matvec(op, x, NULL, 0, Ap, 0, NULL))) return rc;
+    k_cg_init<<<g, GA_NT, 0, fh_stream()>>>(n, B, Ap, r, p, op->part);
+    FH_LAUNCH_CHECK();
+    k_cg_scal<<<1, GA_NT, 0, fh_stream()>>>((int)g, op->part, op->scal, inv, 0);
+    FH_LAUNCH_CHECK();
+    op->kit = 0;
+    op->have_beta = 0;
+    return read_norm(op, norm_res_host);
+}
+
+// up to `nsteps` CG iterations (solver.py:123-136), stopping early when norm_res <= tol.
+// Per iteration: 5 pipeline kernels (S1 carries p = r + beta p, S5 carries <p,Ap>), the x/r update
+// with <r,r>, two single-CTA scalar kernels, and one 8-byte read-back of the residual norm.
+extern "C" int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
+                           double* norm_res_host, double* hist_host) {
+    FH_REQUIRE(op && x && vecs && done_host && norm_res_host, "fh_cg_steps: null argument");
+    const int64_t n = (int64_t)op->D * op->plan->nreal;
+    const double inv = 1.0 / (double)op->plan->nreal;
+    double* r = vecs;
+    double* p = vecs + n;
+    double* Ap = vecs + 2 * n;
+    const unsigned g = ga_grid(n / 2 + 1);
     cudaStream_t s = fh_stream();
     int rc;
-    // Ax = Afun(x0); R = B - Ax; P = R; rr = scal(R, R)
-    if ((rc = fh_ga_apply(op, x, Ap))) return rc;
-    k_cg_init<<<g, GA_NT, 0, s>>>(n, B, Ap, r, p, op->part);
-    FH_LAUNCH_CHECK();
-    k_cg_scal<<<1, GA_NT, 0, s>>>((int)g, op->part, op->scal, inv, 0);
-    FH_LAUNCH_CHECK();
-    double norm_res;
-    if ((rc = read_norm(op, &norm_res))) return rc;
-    int64_t kit = 0;
-    if (hist_host && hist_cap > 0) hist_host[0] = norm_res;
-    while (norm_res > tol && kit < maxiter) {
-        ++kit;
-        if ((rc = fh_ga_apply(op, p, Ap))) return rc;
-        k_dot_part<<<g, GA_NT, 0, s>>>(n, p, Ap, op->part);
+    double norm_res = *norm_res_host;
+    int64_t done = 0;
+    while (norm_res > tol && done < nsteps) {
+        int np = 0;
+        if ((rc = ga_matvec(op, p, r, op->have_beta, Ap, 1, &np))) return rc;
+        k_cg_scal<<<1, GA_NT, 0, s>>>(np, op->part, op->scal, inv, 1);
         FH_LAUNCH_CHECK();
-        k_cg_scal<<<1, GA_NT, 0, s>>>((int)g, op->part, op->scal, inv, 1);
-        FH_LAUNCH_CHECK();
-        k_cg_update<<<g, GA_NT, 0, s>>>(n, x, r, p, Ap, op->scal, op->part);
+        if (n % 2 == 0)
+            k_cg_update<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap,
+                                            op->scal, op->part);
+        else
+            k_cg_update1<<<g, GA_NT, 0, s>>>(n, x, r, p, Ap, op->scal, op->part);
         FH_LAUNCH_CHECK();
         k_cg_scal<<<1, GA_NT, 0, s>>>((int)g, op->part, op->scal, inv, 2);
         FH_LAUNCH_CHECK();
-        k_cg_pupdate<<<g, GA_NT, 0, s>>>(n, p, r, op->scal);
-        FH_LAUNCH_CHECK();
+        op->have_beta = 1;  // P = R + beta P is folded into the next S1
         if ((rc = read_norm(op, &norm_res))) return rc;
+        if (hist_host) hist_host[done] = norm_res;
+        ++done;
+        ++op->kit;
+    }
+    *done_host = done;
+    *norm_res_host = norm_res;
+    return FH_OK;
+}
+
+extern "C" int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t maxiter, double* vecs,
+                     int64_t* kit_host, double* norm_res_host, double* hist_host, int64_t hist_cap) {
+    FH_REQUIRE(op && B && x && vecs && kit_host && norm_res_host, "fh_cg: null argument");
+    FH_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)vecs & 15) == 0 && ((uintptr_t)B & 15) == 0,
+               "fh_cg: buffers must be 16-byte aligned");
+    int rc;
+    double norm_res = 0.0;
+    if ((rc = fh_cg_begin(op, B, x, vecs, &norm_res))) return rc;
+    if (hist_host && hist_cap > 0) hist_host[0] = norm_res;
+    int64_t kit = 0;
+    while (norm_res > tol && kit < maxiter) {
+        int64_t done = 0;
+        double h = 0.0;
+        if ((rc = fh_cg_steps(op, x, vecs, tol, 1, &done, &norm_res, &h))) return rc;
+        kit += done;
         if (hist_host && kit < hist_cap) hist_host[kit] = norm_res;
     }
     *kit_host = kit;
@@ -383,7 +677,7 @@ extern "C" int fh_richardson(fh_ga* op, const double* B, double* x, double alpha
     int64_t kit = 0;
     while (norm_res > tol && kit < maxiter) {
         ++kit;
-        if ((rc = fh_ga_apply(op, x, Ax))) return rc;
+        if ((rc = ga_matvec(op, x, NULL, 0, Ax, 0, NULL))) return rc;
         k_rich_update<<<g, GA_NT, 0, s>>>(n, x, B, Ax, omega, op->part);
         FH_LAUNCH_CHECK();
         k_cg_scal<<<1, GA_NT, 0, s>>>((int)g, op->part, op->scal, inv, 0);

@@ -14,7 +14,7 @@ struct fh_plan {
 };
 
 // kernels launchers shared between translation units
-int fh_launch_r2c_last(const fh_plan* p, const double* x, cplx* X, int64_t nlines);
-int fh_launch_c2r_last(const fh_plan* p, const cplx* X, double* x, int64_t nlines, double scale);
+int fh_launch_r2c_last(const fh_plan* p, const double* x, cplx* X, int64_t nlines, int pitch);
+int fh_launch_c2r_last(const fh_plan* p, const cplx* X, double* x, int64_t nlines, int pitch, double scale);
 int fh_launch_c2c_strided(const AxisDesc& ax, const cplx* in, cplx* out, int64_t outer, int64_t inner, bool inverse,
                           double scale);

@@ -127,11 +127,20 @@ int fh_ga_create(fh_ga** op, const fh_plan* plan, int D, const double* A, int a_
                  double* work);
 int fh_ga_destroy(fh_ga* op);
 int fh_ga_apply(fh_ga* op, const double* x, double* y);
+/* flags: bit0/1/2 = register-resident power-of-two kernels on the last axis / axis 1 / axis 0 */
+int fh_ga_config(const fh_ga* op, int* flags, int* pitch, int* mid_T);
+/* run one stage (1..5) of the pipeline: S1 A.x + R2C, S2 C2C axis 1, S3 axis 0 + G^, S4, S5 C2R (+<x,y>) */
+int fh_ga_stage(fh_ga* op, int stage, const double* x, double* y);
 /* vecs: 3*D*prod(N) doubles of scratch (r, p, Ap); x holds x0 on entry, the solution on exit;
  * hist_host (optional, hist_cap entries) receives the residual norm after every iteration,
  * entry 0 = initial residual                                                          */
 int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t maxiter, double* vecs, int64_t* kit_host,
           double* norm_res_host, double* hist_host, int64_t hist_cap);
+/* the same loop in two calls: begin = initial residual (one operator application), steps = up to
+ * nsteps iterations (stops early at norm_res <= tol); *norm_res_host carries the state in between */
+int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, double* norm_res_host);
+int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
+                double* norm_res_host, double* hist_host);
 /* vecs: 2*D*prod(N) doubles */
 int fh_richardson(fh_ga* op, const double* B, double* x, double alpha, double tol, int64_t maxiter, double* vecs,
                   int64_t* kit_host, double* norm_res_host);

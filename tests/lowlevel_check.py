@@ -195,7 +195,11 @@ cases = [((6, 5), (1.0, 2.0), 0, (0, 0, 0, 1, 0, 0)), ((5, 5), (1.0, 1.0), 1, (0
          ((6, 4), (1.0, 0.5), 1, (0, 1, -1, 1, 0, 0)),
          ((6, 5, 4), (1.0, 2.0, 0.5), 0, (0, 1, 0, -1, 0, 0)), ((8, 8, 8), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)),
          ((9, 9, 9), (1, 1, 1), 1, (0, 1, -1, 1, 0, 0)), ((6, 6, 6), (1, 1, 1), 1, (0.3, 0.2, 0.5, 0.7, 1.5, -0.5)),
-         ((16, 16, 16), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((32, 32, 32), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0))]
+         ((16, 16, 16), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((32, 32, 32), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0)),
+         ((64, 64, 64), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((64, 128, 64), (1, 2, 1), 0, (0, 1, 0, -1, 0, 0)),
+         ((128, 64, 256), (1, 1, 1), 1, (0, 1, -1, 1, 0, 0)), ((64, 64), (1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         ((128, 256), (1, 1), 0, (0, 0, 0, 1, 0, 0)), ((64, 20, 128), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0)),
+         ((12, 64, 64), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0))]
 for N, Y, kind, coef in cases:
     d = len(N)
     D = d if kind == 0 else d*(d+1)//2
@@ -259,7 +263,7 @@ for N, Y, kind, coef in cases:
             report('cg kit N=%s kind=%d (ref %d, got %d)' % (N, kind, kit, kk.value), abs(kit-kk.value), 0)
             report('cg solution', np.abs(xs.cpu().numpy()-xx).max()/max(np.abs(xx).max(), 1e-300), 1e-9)
             m = min(kit, kk.value)+1
-            report('cg residual history', np.max(np.abs(np.array(hh[:m])-np.array(hist[:m]))/np.array(hist[:m])), 1e-6)
+            report('cg residual history', np.max(np.abs(np.array(hh[:m])-np.array(hist[:m]))/hist[0]), 1e-12)
         lib.fh_ga_destroy(op)
         lib.fh_plan_destroy(p)
 
@@ -297,8 +301,32 @@ if '--time' in sys.argv:
         work = torch.zeros(lib.fh_ga_work_doubles(p, D), dtype=torch.float64, device=dev)
         op = C.c_void_p()
         L.check(lib.fh_ga_create(C.byref(op), p, D, ptr(A), 0, C.byref(g), ptr(work)))
+        fl, pi, mt = C.c_int(), C.c_int(), C.c_int()
+        L.check(lib.fh_ga_config(op, C.byref(fl), C.byref(pi), C.byref(mt)))
+        print('ga config: fast flags=%d pitch=%d mid_T=%d' % (fl.value, pi.value, mt.value))
         t = timeit(lambda: L.check(lib.fh_ga_apply(op, ptr(x), ptr(y))))
         print('ga_apply %d^3 D=6: %.3f ms' % (n, t))
+        Fs = 16*D*n*n*pi.value
+        CA = 8*D*D*nreal
+        alg = {1: F+CA+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
+        for st in range(1, 6):
+            t = timeit(lambda: L.check(lib.fh_ga_stage(op, st, ptr(x), ptr(y))), reps=10)
+            print('  stage %d: %.3f ms -> %.0f GB/s' % (st, t, alg[st]/t/1e6))
+        B = torch.randn((D,)+N, dtype=torch.float64, device=dev)
+        xs = torch.zeros((D,)+N, dtype=torch.float64, device=dev)
+        vecs = torch.zeros(3*D*nreal, dtype=torch.float64, device=dev)
+        nr = C.c_double()
+        L.check(lib.fh_cg_begin(op, ptr(B), ptr(xs), ptr(vecs), C.byref(nr)))
+        done = C.c_int64()
+        L.check(lib.fh_cg_steps(op, ptr(xs), ptr(vecs), 0.0, 3, C.byref(done), C.byref(nr), None))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.check(lib.fh_cg_steps(op, ptr(xs), ptr(vecs), 0.0, 20, C.byref(done), C.byref(nr), None))
+        torch.cuda.synchronize()
+        t = (time.perf_counter()-t0)/20*1e3
+        print('CG iteration %d^3 D=6: %.3f ms -> %.1f it/s, %.3e DOF/s, %.0f GB/s of the 15F+C_A(sym) model'
+              % (n, t, 1e3/t, D*nreal*1e3/t, (15*F+8*21*nreal)/t/1e6))
+        del B, xs, vecs
         out = torch.zeros_like(x)
         t = timeit(lambda: L.check(lib.fh_axpby(D*nreal, 1.0, ptr(x), 2.0, ptr(y), ptr(out))))
         print('axpby %d^3 D=6: %.3f ms -> %.0f GB/s' % (n, t, 3*F/t/1e6))
