@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(T* FastCfg<N>::TPL) k_c2c_fast(const cplx* __r
 // data [D][N][inner]; one CTA owns T consecutive inner positions of all D components.
 // blockDim = D * T * TPL.  nh = valid entries per spectrum row, pitch = padded row length.
 template <int N, int T, int KIND, int DIM>
-__global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) * T * FastCfg<N>::TPL)
+__global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) * T * FastCfg<N>::TPL,
+                                  (T <= 2 ? 3 : 1))
     k_mid_green_fast(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
                      int pitch) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
@@ -182,14 +183,17 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 // lines as SoA (re plane, im plane), each line padded by one element per 16 (conflict-free
 // radix-16 scatter).  blockDim = NP * TPL.
 //   mode bit 0: p = r + beta*p first (the CG direction update, solver.py:132), beta = scal[3]
-//   A layout 0: full [D][D][n];  -1: no coefficient multiply (plain forward transform of x)
+//   A layout 0: full [D][D][n];  1: symmetric — only the upper triangle of the full array is read;
+//   2: piecewise constant — one byte per voxel indexes a table of <= 16 DxD matrices held in shared
+//   memory (detected by fh_ga_create, e.g. inclusion-type microstructures);  -1: no multiply
 __device__ __forceinline__ int pidx(int row) { return row + (row >> 4); }
 
 template <int N, int D, int TRW, int ALAY>
 __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
-    k_fwd_last_fast(const double* __restrict__ A, double* __restrict__ p, const double* __restrict__ r,
-                    const double* __restrict__ scal, int pupdate, cplx* __restrict__ spec,
-                    const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+    k_fwd_last_fast(const double* __restrict__ A, const unsigned char* __restrict__ phase,
+                    const double* __restrict__ lut, int nphase, double* __restrict__ p,
+                    const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
+                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
     constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
     constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
     constexpr int NT = NP * TPL;
@@ -200,10 +204,21 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     const int64_t n = nrows * N;  // voxels per component
     const double beta = pupdate ? scal[3] : 0.0;
+    __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
+    if (ALAY == 2) {
+        for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
+        __syncthreads();
+    }
     // phase 0: sigma = A p on TRW x N voxels, two voxels per thread and step (16-byte accesses)
     for (int v = threadIdx.x; v < TRW * (N / 2); v += NT) {
         const int row = v / (N / 2), i2 = 2 * (v - row * (N / 2));
         const int64_t gv = (row0 + row) * N + i2;
+        int ph0 = 0, ph1 = 0;
+        if (ALAY == 2) {
+            const uchar2 ph = *reinterpret_cast<const uchar2*>(phase + gv);
+            ph0 = ph.x * D * D;
+            ph1 = ph.y * D * D;
+        }
         double2 pv[D];
 #pragma unroll
         for (int jj = 0; jj < D; ++jj) {
@@ -224,7 +239,15 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
                 s = make_double2(0.0, 0.0);
 #pragma unroll
                 for (int jj = 0; jj < D; ++jj) {
-                    const double2 a = *reinterpret_cast<const double2*>(A + ((size_t)i * D + jj) * n + gv);
+                    double2 a;
+                    if (ALAY == 2) {
+                        a = make_double2(slut[ph0 + i * D + jj], slut[ph1 + i * D + jj]);
+                    } else if (ALAY == 1) {  // symmetric: (i,j) and (j,i) read the same upper-triangle entry
+                        const int lo = i < jj ? i : jj, hi = i < jj ? jj : i;
+                        a = *reinterpret_cast<const double2*>(A + ((size_t)lo * D + hi) * n + gv);
+                    } else {
+                        a = *reinterpret_cast<const double2*>(A + ((size_t)i * D + jj) * n + gv);
+                    }
                     s.x += a.x * pv[jj].x;
                     s.y += a.y * pv[jj].y;
                 }
@@ -308,23 +331,42 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     double* zim = smd + NP * NPAD;
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     // phase 0: Z = X_a + i X_b on the full circle (Hermitian completion), natural order
-    for (int it = threadIdx.x; it < NP * nh; it += NT) {
-        const int pr = it / nh, k = it - pr * nh;
-        const int La = 2 * pr, Lb = 2 * pr + 1;
-        const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
-        cplx a = spec[((size_t)ca * nrows + row0 + ra) * pitch + k];
-        cplx b = spec[((size_t)cb * nrows + row0 + rb) * pitch + k];
-        if (k == 0 || 2 * k == N) {
-            a.y = 0.0;
-            b.y = 0.0;
+    // (U independent 16-byte loads per thread are issued before any is consumed)
+    constexpr int U = 4;
+    for (int it0 = threadIdx.x; it0 < NP * nh; it0 += U * NT) {
+        cplx a[U], b[U];
+        int prs[U], ks[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int it = it0 + u * NT;
+            prs[u] = -1;
+            if (it < NP * nh) {
+                const int pr = it / nh, k = it - pr * nh;
+                const int La = 2 * pr, Lb = 2 * pr + 1;
+                const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
+                a[u] = spec[((size_t)ca * nrows + row0 + ra) * pitch + k];
+                b[u] = spec[((size_t)cb * nrows + row0 + rb) * pitch + k];
+                prs[u] = pr;
+                ks[u] = k;
+            }
         }
-        double* qre = zre + pr * NPAD;
-        double* qim = zim + pr * NPAD;
-        qre[pidx(k)] = a.x - b.y;
-        qim[pidx(k)] = a.y + b.x;
-        if (k > 0 && 2 * k != N) {
-            qre[pidx(N - k)] = a.x + b.y;
-            qim[pidx(N - k)] = -a.y + b.x;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (prs[u] < 0) continue;
+            const int k = ks[u];
+            cplx av = a[u], bv = b[u];
+            if (k == 0 || 2 * k == N) {
+                av.y = 0.0;
+                bv.y = 0.0;
+            }
+            double* qre = zre + prs[u] * NPAD;
+            double* qim = zim + prs[u] * NPAD;
+            qre[pidx(k)] = av.x - bv.y;
+            qim[pidx(k)] = av.y + bv.x;
+            if (k > 0 && 2 * k != N) {
+                qre[pidx(N - k)] = av.x + bv.y;
+                qim[pidx(N - k)] = -av.y + bv.x;
+            }
         }
     }
     __syncthreads();
@@ -369,4 +411,142 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) part[blockIdx.x] = acc;
     }
+}
+
+// ------------------------------------------------------------------ axis 0 + G^, software-pipelined
+// Persistent variant of k_mid_green_fast: one CTA per SM loops over tiles; the next tile is
+// fetched with cp.async (16-byte, L2-only) into the second shared-memory buffer while the current
+// one is transformed, so the HBM stream overlaps the FP64 / shared-memory work of the same SM.
+// The forward transform is decimation-in-frequency and the inverse its mirror, so every stage is
+// in place (no transposing stage, no extra barrier); between them the spectrum sits in shared
+// memory in digit-reversed row order, which the Green stage undoes arithmetically:
+//   F1: rows {j + r*Rb}: y = DFT_Ra(x) , y[q] *= w_N^(q*j)        (in place)
+//   F2: rows {q*Rb + s}: X[q + Ra*s] = DFT_Rb(y_q)[s]             (in place; row q*Rb+s holds k0 = q + Ra*s)
+//   G^ on every row, I2 = inverse of F2, I1 = inverse of F1 -> global.
+// Rows are padded by one row per 16 so the block-strided F2/I2 accesses are conflict free.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NG>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(NG));
+}
+
+template <int N, int T, int KIND, int DIM>
+__global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) * T * FastCfg<N>::TPL, 1)
+    k_mid_green_pipe(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
+                     int pitch, int ntiles) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int Ra = FastCfg<N>::R1, Rb = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
+    constexpr int NPR = N + N / 16;        // padded rows per component
+    constexpr int BUF = D * NPR * T;       // complex elements per buffer
+    constexpr int NT = D * T * TPL;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf0 = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int t = threadIdx.x % T;
+    const int j = (threadIdx.x / T) % TPL;
+    const int c = threadIdx.x / (T * TPL);
+
+    auto prefetch = [&](int tile, cplx* buf) {
+        const int64_t i0 = (int64_t)tile * T;
+#pragma unroll 4
+        for (int e = threadIdx.x; e < D * N * T; e += NT) {
+            const int tt = e % T, row = (e / T) % N, cc = e / (T * N);
+            cp_async16(buf + (cc * NPR + pidx(row)) * T + tt, data + ((int64_t)cc * N + row) * inner + i0 + tt);
+        }
+    };
+
+    int it = 0;
+    if ((int)blockIdx.x < ntiles) prefetch(blockIdx.x, buf0);
+    cp_async_commit();
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+        cplx* cur = buf0 + (it & 1) * BUF;
+        const int next = tile + gridDim.x;
+        if (next < ntiles) prefetch(next, buf0 + ((it + 1) & 1) * BUF);
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncthreads();
+        cplx* sc = cur + c * NPR * T + t;
+        const int64_t i0 = (int64_t)tile * T;
+        // F1
+        if (j < Rb) {
+            cplx v[Ra];
+#pragma unroll
+            for (int r = 0; r < Ra; ++r) v[r] = sc[pidx(j + r * Rb) * T];
+            Bfly<Ra, false>::run(v);
+#pragma unroll
+            for (int q = 1; q < Ra; ++q) v[q] = cmul(v[q], ldtw(tw, q * j, false));
+#pragma unroll
+            for (int q = 0; q < Ra; ++q) sc[pidx(j + q * Rb) * T] = v[q];
+        }
+        __syncthreads();
+        // F2
+        if (j < Ra) {
+            cplx v[Rb];
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) v[s] = sc[pidx(j * Rb + s) * T];
+            Bfly<Rb, false>::run(v);
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) sc[pidx(j * Rb + s) * T] = v[s];
+        }
+        __syncthreads();
+        // G^: row = q*Rb + s holds frequency index q + Ra*s
+        for (int idx = threadIdx.x; idx < N * T; idx += NT) {
+            const int row = idx / T, tt = idx - row * T;
+            const int q = row / Rb, s = row - q * Rb;
+            int k[3];
+            k[0] = fh_freq(q + Ra * s, N);
+            const int64_t ii = i0 + tt;
+            bool valid = true;
+            if (DIM == 3) {
+                const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+                k[1] = fh_freq(i1, g.N[1]);
+                k[2] = fh_freq(i2, g.N[2]);
+                valid = i2 < nh;
+            } else {
+                k[1] = fh_freq((int)ii, g.N[1]);
+                k[2] = 0;
+                valid = (int)ii < nh;
+            }
+            cplx* sr = cur + pidx(row) * T + tt;
+            cplx e[D];
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * NPR * T];
+            if (valid) {
+                green_apply<KIND, DIM>(g, k, e);
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) sr[cc * NPR * T] = e[cc];
+        }
+        __syncthreads();
+        // I2
+        if (j < Ra) {
+            cplx v[Rb];
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) v[s] = sc[pidx(j * Rb + s) * T];
+            Bfly<Rb, true>::run(v);
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) sc[pidx(j * Rb + s) * T] = v[s];
+        }
+        __syncthreads();
+        // I1 -> global
+        if (j < Rb) {
+            cplx v[Ra];
+#pragma unroll
+            for (int q = 0; q < Ra; ++q) v[q] = sc[pidx(j + q * Rb) * T];
+#pragma unroll
+            for (int q = 1; q < Ra; ++q) v[q] = cmul(v[q], ldtw(tw, q * j, true));
+            Bfly<Ra, true>::run(v);
+            cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+#pragma unroll
+            for (int r = 0; r < Ra; ++r) gp[(int64_t)(j + r * Rb) * inner] = v[r];
+        }
+        __syncthreads();  // the buffer may be refilled by the prefetch of the next iteration
+    }
+    cp_async_wait<0>();
 }

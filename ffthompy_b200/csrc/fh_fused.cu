@@ -23,13 +23,17 @@
 int fh_fill_green(GreenDesc& g, const fh_green* in);
 
 #define GA_NT 256
-#define GA_MAXPART 16384
+#define GA_MAXPART 65536
 
 struct fh_ga {
     const fh_plan* plan;
     int D;
     const double* A;
     int a_layout;
+    int a_mode;            // how S1 reads the coefficients: 0 full, 1 symmetric (upper triangle), 2 phase table
+    unsigned char* phase;  // [prod(N)] phase index per voxel (a_mode 2), owned by the operator
+    double* lut;           // [nphase][D][D]
+    int nphase;
     GreenDesc g;
     int pitch;       // padded spectrum row length (complex elements)
     int64_t nrows;   // prod(N[:-1])
@@ -39,7 +43,7 @@ struct fh_ga {
     cplx* spec;     // [D][nrows][pitch]
     // configuration
     bool fast_last, fast_mid1, fast_mid0;
-    int mid_T, trw;
+    int mid_T, trw, mid_pipe;
     // device scalars / partial sums of the Krylov loops
     double* scal;  // [16]: rr, pAp, alpha, beta, norm_res
     double* part;  // [GA_MAXPART]
@@ -213,10 +217,34 @@ static int launch_mid_fast_NT(fh_ga* op) {
     return FH_OK;
 }
 
+template <int N, int T, int KIND, int DIM>
+static int launch_mid_pipe_NT(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const fh_plan* p = op->plan;
+    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const size_t smem = (size_t)2 * D * (N + N / 16) * T * sizeof(cplx);
+    const int ntiles = (int)(inner / T);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_pipe<N, T, KIND, DIM>, smem))) return rc;
+    const int grid = ntiles < fh_num_sms() ? ntiles : fh_num_sms();
+    k_mid_green_pipe<N, T, KIND, DIM><<<grid, D * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
+        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch, ntiles);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
 template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
+    if (op->mid_pipe && T == 4) {
+        constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+        if ((size_t)2 * D * (N + N / 16) * 4 * sizeof(cplx) <= (size_t)fh_max_smem_optin()) {
+            if (N == 64) return launch_mid_pipe_NT<64, 4, KIND, DIM>(op);
+            if (N == 128) return launch_mid_pipe_NT<128, 4, KIND, DIM>(op);
+            if (N == 256) return launch_mid_pipe_NT<256, 4, KIND, DIM>(op);
+        }
+    }
 #define FH_MID_CASE(n, t) \
     if (N == n && T == t) return launch_mid_fast_NT<n, t, KIND, DIM>(op);
     FH_MID_CASE(64, 2)
@@ -229,26 +257,29 @@ static int launch_mid_fast(fh_ga* op) {
     return fh_set_error(FH_ERR_UNSUPPORTED, "no fast Green kernel for N0=%d T=%d", N, T);
 }
 
-template <int N, int D, int TRW>
-static int launch_fwd_last_NT(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+template <int N, int D, int TRW, int ALAY>
+static int launch_fwd_last_NTA(fh_ga* op, double* p, const double* r, int pupdate) {
     constexpr int NP = D * TRW / 2, NPAD = N + N / 16;
     const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
     const unsigned nblk = (unsigned)(op->nrows / TRW);
     const int nt = NP * FastCfg<N>::TPL;
     const fh_plan* pl = op->plan;
-    const cplx* tw = pl->ax[pl->dim - 1].tw;
     int rc;
-    if (withA) {
-        if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, 0>, smem))) return rc;
-        k_fwd_last_fast<N, D, TRW, 0><<<nblk, nt, smem, fh_stream()>>>(op->A, p, r, op->scal, pupdate, op->spec, tw,
-                                                                        op->nrows, pl->nh, op->pitch);
-    } else {
-        if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, -1>, smem))) return rc;
-        k_fwd_last_fast<N, D, TRW, -1><<<nblk, nt, smem, fh_stream()>>>(op->A, p, r, op->scal, pupdate, op->spec, tw,
-                                                                         op->nrows, pl->nh, op->pitch);
-    }
+    if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, ALAY>, smem))) return rc;
+    k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->nphase, p, r,
+                                                                       op->scal, pupdate, op->spec,
+                                                                       pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
+                                                                       op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
+}
+
+template <int N, int D, int TRW>
+static int launch_fwd_last_NT(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    if (!withA) return launch_fwd_last_NTA<N, D, TRW, -1>(op, p, r, pupdate);
+    if (op->a_mode == 2) return launch_fwd_last_NTA<N, D, TRW, 2>(op, p, r, pupdate);
+    if (op->a_mode == 1) return launch_fwd_last_NTA<N, D, TRW, 1>(op, p, r, pupdate);
+    return launch_fwd_last_NTA<N, D, TRW, 0>(op, p, r, pupdate);
 }
 
 template <int N, int D, int TRW>
@@ -273,7 +304,11 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     do {                                                                     \
         const int N_ = op->plan->N[op->plan->dim - 1];                       \
         const int D_ = op->D;                                                \
-        if (D_ == 6) {                                                       \
+        if (D_ == 6 && op->trw == 2) {                                       \
+            if (N_ == 64) return FN<64, 6, 2>(__VA_ARGS__);                  \
+            if (N_ == 128) return FN<128, 6, 2>(__VA_ARGS__);                \
+            if (N_ == 256) return FN<256, 6, 2>(__VA_ARGS__);                \
+        } else if (D_ == 6) {                                                \
             if (N_ == 64) return FN<64, 6, 4>(__VA_ARGS__);                  \
             if (N_ == 128) return FN<128, 6, 4>(__VA_ARGS__);                \
             if (N_ == 256) return FN<256, 6, 4>(__VA_ARGS__);                \
@@ -296,6 +331,99 @@ static int launch_inv_last_fast(fh_ga* op, double* y, const double* pdot, int* n
     FH_LAST_DISPATCH(launch_inv_last_NT, op, y, pdot, npart);
 }
 static int trw_for(int D) { return D == 6 ? 4 : 8; }
+
+// ------------------------------------------------------------------ coefficient analysis (once per operator)
+// exact symmetry check: flag != 0 if any A_ij != A_ji
+__global__ void k_sym_check(int64_t n, int D, const double* __restrict__ A, int* __restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+        for (int i = 0; i < D; ++i)
+            for (int j = i + 1; j < D; ++j)
+                if (A[((size_t)i * D + j) * n + v] != A[((size_t)j * D + i) * n + v]) *flag = 1;
+}
+// phase[v] = index of the table matrix that equals A[:, :, v] exactly; voxels matching none
+// report the smallest such index through atomicMin
+__global__ void k_phase_match(int64_t n, int DD, const double* __restrict__ A, const double* __restrict__ lut,
+                              int nph, unsigned char* __restrict__ phase, unsigned long long* __restrict__ first) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        int found = -1;
+        for (int m = 0; m < nph && found < 0; ++m) {
+            bool eq = true;
+            for (int e = 0; e < DD && eq; ++e) eq = (A[(size_t)e * n + v] == lut[m * DD + e]);
+            if (eq) found = m;
+        }
+        if (found >= 0)
+            phase[v] = (unsigned char)found;
+        else
+            atomicMin(first, (unsigned long long)v);
+    }
+}
+__global__ void k_lut_fetch(int64_t n, int DD, const double* __restrict__ A, int64_t v, double* __restrict__ dst) {
+    const int e = threadIdx.x;
+    if (e < DD) dst[e] = A[(size_t)e * n + v];
+}
+
+#define FH_MAX_PHASES 16
+static int analyse_coefficients(fh_ga* op) {
+    const int D = op->D, DD = D * D;
+    const int64_t n = op->plan->nreal;
+    const int want = env_int("FH_AMODE", -1);  // -1 auto, 0 full, 1 sym, 2 phase table
+    op->a_mode = 0;
+    op->phase = NULL;
+    op->lut = NULL;
+    op->nphase = 0;
+    if (want == 0 || !op->fast_last) return FH_OK;
+    const unsigned grid = (unsigned)(fh_num_sms() * 8);
+    if ((want < 0 || want == 2) && n % 2 == 0) {
+        unsigned long long* first = NULL;
+        FH_CUDA(cudaMalloc((void**)&first, sizeof(unsigned long long)));
+        FH_CUDA(cudaMalloc((void**)&op->phase, (size_t)n));
+        FH_CUDA(cudaMalloc((void**)&op->lut, sizeof(double) * FH_MAX_PHASES * DD));
+        int nph = 0;
+        bool ok = false;
+        for (int round = 0; round <= FH_MAX_PHASES; ++round) {
+            const unsigned long long none = ~0ULL;
+            FH_CUDA(cudaMemcpyAsync(first, &none, sizeof(none), cudaMemcpyHostToDevice, fh_stream()));
+            k_phase_match<<<grid, 256, 0, fh_stream()>>>(n, DD, op->A, op->lut, nph, op->phase, first);
+            FH_LAUNCH_CHECK();
+            unsigned long long f = 0;
+            FH_CUDA(cudaMemcpyAsync(&f, first, sizeof(f), cudaMemcpyDeviceToHost, fh_stream()));
+            FH_CUDA(cudaStreamSynchronize(fh_stream()));
+            if (f == none) {
+                ok = true;
+                break;
+            }
+            if (nph == FH_MAX_PHASES) break;
+            k_lut_fetch<<<1, 64, 0, fh_stream()>>>(n, DD, op->A, (int64_t)f, op->lut + (size_t)nph * DD);
+            FH_LAUNCH_CHECK();
+            ++nph;
+        }
+        cudaFree(first);
+        if (ok) {
+            op->a_mode = 2;
+            op->nphase = nph;
+            return FH_OK;
+        }
+        cudaFree(op->phase);
+        cudaFree(op->lut);
+        op->phase = NULL;
+        op->lut = NULL;
+    }
+    if (want < 0 || want == 1) {
+        int* flag = NULL;
+        FH_CUDA(cudaMalloc((void**)&flag, sizeof(int)));
+        FH_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), fh_stream()));
+        k_sym_check<<<grid, 256, 0, fh_stream()>>>(n, D, op->A, flag);
+        FH_LAUNCH_CHECK();
+        int h = 1;
+        FH_CUDA(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, fh_stream()));
+        FH_CUDA(cudaStreamSynchronize(fh_stream()));
+        cudaFree(flag);
+        if (h == 0) op->a_mode = 1;
+    }
+    return FH_OK;
+}
 
 // ------------------------------------------------------------------ operator object
 static int64_t sigma_doubles(const fh_plan* p, int D) { return ((int64_t)D * p->nreal + 15) / 16 * 16; }
@@ -336,10 +464,12 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     const int use_fast = env_int("FH_FAST", 1);
     const int d = plan->dim;
     op->trw = trw_for(D);
+    if (D == 6 && env_int("FH_TRW", 4) == 2) op->trw = 2;
     op->fast_last = use_fast && fh_fast_len(plan->N[d - 1]) && (op->nrows % op->trw == 0);
     op->fast_mid1 = use_fast && d == 3 && fh_fast_len(plan->N[1]);
     op->fast_mid0 = use_fast && fh_fast_len(plan->N[0]);
     op->mid_T = env_int("FH_MID_T", 4);
+    op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
     if ((size_t)D * plan->N[0] * op->mid_T * sizeof(cplx) > (size_t)fh_max_smem_optin()) op->mid_T = 2;
     cudaError_t e = cudaMalloc((void**)&op->scal, sizeof(double) * (16 + GA_MAXPART));
@@ -352,22 +482,31 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
         return fh_set_error(FH_ERR_CUDA, "fh_ga_create: %s", cudaGetErrorString(e));
     }
     op->part = op->scal + 16;
+    if ((rc = analyse_coefficients(op))) {
+        fh_ga_destroy(op);
+        return rc;
+    }
     *out = op;
     return FH_OK;
 }
 
 extern "C" int fh_ga_destroy(fh_ga* op) {
     if (!op) return FH_OK;
+    if (op->phase) cudaFree(op->phase);
+    if (op->lut) cudaFree(op->lut);
     cudaFree(op->scal);
     cudaFreeHost(op->pinned);
     free(op);
     return FH_OK;
 }
 
-// which kernels an operator uses: bit0 fast last axis, bit1 fast axis 1, bit2 fast axis 0
+// which kernels an operator uses: bit0 fast last axis, bit1 fast axis 1, bit2 fast axis 0;
+// bits 4-5 coefficient mode (0 full, 1 symmetric, 2 phase table), bits 8.. number of phases
 extern "C" int fh_ga_config(const fh_ga* op, int* flags, int* pitch, int* mid_T) {
     FH_REQUIRE(op, "fh_ga_config: null argument");
-    if (flags) *flags = (op->fast_last ? 1 : 0) | (op->fast_mid1 ? 2 : 0) | (op->fast_mid0 ? 4 : 0);
+    if (flags)
+        *flags = (op->fast_last ? 1 : 0) | (op->fast_mid1 ? 2 : 0) | (op->fast_mid0 ? 4 : 0) | (op->a_mode << 4) |
+                 (op->nphase << 8);
     if (pitch) *pitch = op->pitch;
     if (mid_T) *mid_T = op->mid_T;
     return FH_OK;

@@ -77,10 +77,11 @@ __device__ __forceinline__ void green_scalar(const GreenDesc& g, const int* k, c
     }
 }
 
-// Real-valued core of the Mandel-elastic multiplier (applied to re and im).
+// Real-valued core of the Mandel-elastic multiplier (applied to re and im).  xi = frequency,
+// inv = 1/|xi|^2, v = Mandel(xi (x) xi)/|xi|^2 (shared between the real and imaginary part).
 template <int DIM>
-__device__ __forceinline__ void green_elastic_real(const GreenDesc& g, const double* n /*xi*/, double inv /*1/|xi|^2*/,
-                                                   double* e) {
+__device__ __forceinline__ void green_elastic_real(const GreenDesc& g, const double* n /*xi*/, double inv,
+                                                   const double* v, double* e) {
     constexpr int D = DIM * (DIM + 1) / 2;
     const double r2 = 0.70710678118654752440;  // 1/sqrt(2)
     const double s2 = 1.41421356237309504880;
@@ -104,22 +105,15 @@ __device__ __forceinline__ void green_elastic_real(const GreenDesc& g, const dou
     nw *= inv;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) w[i] *= inv;
-    // Mandel(n (x) n) and Mandel(n (x) w + w (x) n), n = xi/|xi| folded in through `inv`
-    double v[D], Se[D];
+    // Mandel(n (x) w + w (x) n), n = xi/|xi| folded in through `inv`
+    double Se[D];
 #pragma unroll
-    for (int i = 0; i < DIM; ++i) {
-        v[i] = n[i] * n[i] * inv;
-        Se[i] = 2.0 * n[i] * w[i];
-    }
+    for (int i = 0; i < DIM; ++i) Se[i] = 2.0 * n[i] * w[i];
     if (DIM == 3) {
-        v[3] = s2 * n[1] * n[2] * inv;
-        v[4] = s2 * n[0] * n[2] * inv;
-        v[5] = s2 * n[0] * n[1] * inv;
         Se[3] = s2 * (n[1] * w[2] + w[1] * n[2]);
         Se[4] = s2 * (n[0] * w[2] + w[0] * n[2]);
         Se[5] = s2 * (n[0] * w[1] + w[0] * n[1]);
     } else {
-        v[2] = s2 * n[0] * n[1] * inv;
         Se[2] = s2 * (n[0] * w[1] + w[0] * n[1]);
     }
     const double cHn = g.cH * nw + g.cW * tr;          // multiplies v
@@ -135,6 +129,7 @@ __device__ __forceinline__ void green_elastic_real(const GreenDesc& g, const dou
 template <int DIM>
 __device__ __forceinline__ void green_elastic(const GreenDesc& g, const int* k, cplx* e) {
     constexpr int D = DIM * (DIM + 1) / 2;
+    const double s2 = 1.41421356237309504880;
     double xi[DIM];
     double s = 0.0;
     bool inband = true, zero = true;
@@ -156,14 +151,24 @@ __device__ __forceinline__ void green_elastic(const GreenDesc& g, const int* k, 
         return;
     }
     const double inv = 1.0 / s;
+    double v[D];
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) v[i] = xi[i] * xi[i] * inv;
+    if (DIM == 3) {
+        v[3] = s2 * xi[1] * xi[2] * inv;
+        v[4] = s2 * xi[0] * xi[2] * inv;
+        v[5] = s2 * xi[0] * xi[1] * inv;
+    } else {
+        v[2] = s2 * xi[0] * xi[1] * inv;
+    }
     double re[D], im[D];
 #pragma unroll
     for (int m = 0; m < D; ++m) {
         re[m] = e[m].x;
         im[m] = e[m].y;
     }
-    green_elastic_real<DIM>(g, xi, inv, re);
-    green_elastic_real<DIM>(g, xi, inv, im);
+    green_elastic_real<DIM>(g, xi, inv, v, re);
+    green_elastic_real<DIM>(g, xi, inv, v, im);
 #pragma unroll
     for (int m = 0; m < D; ++m) e[m] = make_double2(re[m], im[m]);
 }

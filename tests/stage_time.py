@@ -1,0 +1,52 @@
+import ctypes as C, os, sys, time
+import numpy as np, torch
+sys.path.insert(0, os.getcwd())
+from ffthompy_b200 import _lib as L
+lib = L.load(); L.check(lib.fh_init(0)); dev = torch.device('cuda:0')
+def ptr(t): return C.c_void_p(t.data_ptr())
+def timeit(fn, reps=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps
+n = int(os.environ.get('BN', '256')); N = (n, n, n); D = 6
+p = C.c_void_p(); L.check(lib.fh_plan_create(C.byref(p), 3, L.i64arr(N)))
+x = torch.randn((D,)+N, dtype=torch.float64, device=dev); y = torch.zeros_like(x)
+mode = os.environ.get('BA', 'phase')
+if mode == 'rand':
+    A = torch.randn((D, D)+N, dtype=torch.float64, device=dev)
+elif mode == 'sym':
+    A = torch.randn((D, D)+N, dtype=torch.float64, device=dev)
+    A = (A+A.transpose(0, 1)).contiguous()
+else:
+    ph = (torch.rand(N, device=dev) < 0.3).to(torch.float64)
+    C0 = torch.eye(D, dtype=torch.float64, device=dev)*2+1
+    C1 = torch.eye(D, dtype=torch.float64, device=dev)*10+5
+    A = (C0[:, :, None, None, None]*(1-ph)+C1[:, :, None, None, None]*ph).contiguous()
+g = L.fh_green(); g.kind = 1; g.dim = 3
+for a in range(3): g.N[a] = n; g.Y[a] = 1.0; g.band[a] = (n-((n+1) % 2)-1)//2
+g.cS, g.cH, g.scale = 1.0, -1.0, 1.0
+work = torch.zeros(lib.fh_ga_work_doubles(p, D), dtype=torch.float64, device=dev)
+op = C.c_void_p(); L.check(lib.fh_ga_create(C.byref(op), p, D, ptr(A), 0, C.byref(g), ptr(work)))
+fl, pi, mt = C.c_int(), C.c_int(), C.c_int(); L.check(lib.fh_ga_config(op, C.byref(fl), C.byref(pi), C.byref(mt)))
+nreal = n**3; F = 8*D*nreal; Fs = 16*D*n*n*pi.value; CA = 8*D*D*nreal
+CA = {'rand': CA, 'sym': 8*21*nreal}.get(mode, nreal)
+alg = {1: F+CA+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
+out = ['A=%s cfg flags=%d pitch=%d midT=%d env=%s' % (mode, fl.value, pi.value, mt.value, {k: v for k, v in os.environ.items() if k.startswith('FH_')})]
+for st in range(1, 6):
+    t = timeit(lambda: L.check(lib.fh_ga_stage(op, st, ptr(x), ptr(y))))
+    out.append('S%d %.3f ms %.0f GB/s' % (st, t, alg[st]/t/1e6))
+t = timeit(lambda: L.check(lib.fh_ga_apply(op, ptr(x), ptr(y))))
+out.append('apply %.3f ms' % t)
+B = torch.randn((D,)+N, dtype=torch.float64, device=dev); xs = torch.zeros_like(B)
+vecs = torch.zeros(3*D*nreal, dtype=torch.float64, device=dev); nr = C.c_double(); done = C.c_int64()
+L.check(lib.fh_cg_begin(op, ptr(B), ptr(xs), ptr(vecs), C.byref(nr)))
+L.check(lib.fh_cg_steps(op, ptr(xs), ptr(vecs), 0.0, 3, C.byref(done), C.byref(nr), None))
+torch.cuda.synchronize(); t0 = time.perf_counter()
+L.check(lib.fh_cg_steps(op, ptr(xs), ptr(vecs), 0.0, 20, C.byref(done), C.byref(nr), None))
+torch.cuda.synchronize(); t = (time.perf_counter()-t0)/20*1e3
+out.append('CG %.3f ms/it %.1f it/s' % (t, 1e3/t))
+print(' | '.join(out))
