@@ -53,7 +53,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu='+self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -242,7 +242,8 @@ def run_ours(args):
     L.check(lib.fh_ga_config(f.handle, C.byref(flags), C.byref(pitch), C.byref(midT)))
     F = 8.*D*nvox
     Fs = 16.*D*n*n*pitch.value
-    CA = 8.*D*D*nvox
+    amode = (flags.value >> 4) & 3
+    CA = {0: 8.*D*D*nvox, 1: 8.*21*nvox, 2: 1.*nvox}[amode]  # bytes of coefficient data S1 actually streams
     alg = {1: F+CA+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
     names = {1: 'S1 A.p + R2C (last axis)', 2: 'S2 C2C axis 1', 3: 'S3 C2C axis 0 + Green + inverse axis 0',
              4: 'S4 inverse C2C axis 1', 5: 'S5 C2R (last axis) + <p,Ap>'}
@@ -330,7 +331,10 @@ def run_ours(args):
             'comparators': {'cufft_rfftn_irfftn_ms': cufft_ms, 'fused_operator_ms': ga_ms,
                             'note': 'cuFFT (torch.fft) forward+inverse of the same (6,n,n,n) field, no A.p / Green / '
                                     'dot work, vs the whole fused operator G.A.p'},
-            'kernels': {'fast_flags': flags.value, 'spectrum_pitch': pitch.value, 'mid_T': midT.value}}
+            'kernels': {'fast_axes_mask': flags.value & 7, 'spectrum_pitch': pitch.value, 'mid_T': midT.value,
+                        'coefficient_mode': {0: 'full DxD array', 1: 'symmetric (upper triangle read)',
+                                             2: 'phase table (1 byte/voxel)'}[(flags.value >> 4) & 3],
+                        'phases': flags.value >> 8}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -340,7 +344,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--n', type=int, default=256)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])

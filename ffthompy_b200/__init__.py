@@ -27,11 +27,11 @@ def install(reference_package='ffthompy'):
     import importlib
     ref = importlib.import_module(reference_package)  # the reference tree must be importable
     from . import tensors, projections, trigpol
-    from .tensors import objects, operators, projection
+    from .tensors import objects, operators, projection, fft
     from .general import solver, solver_pp
     mapping = {
         'tensors': tensors, 'tensors.objects': objects, 'tensors.operators': operators,
-        'tensors.projection': projection, 'projections': projections,
+        'tensors.projection': projection, 'tensors.fft': fft, 'projections': projections,
         'general.solver': solver, 'general.solver_pp': solver_pp, 'trigpol': trigpol,
     }
     for name, mod in mapping.items():

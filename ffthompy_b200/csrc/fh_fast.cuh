@@ -550,3 +550,115 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
     }
     cp_async_wait<0>();
 }
+
+// ------------------------------------------------------------------ axis 0 + G^, two CTAs per SM
+// Same in-place DIF / mirrored-inverse scheme as k_mid_green_pipe, but each CTA has only
+// (D/CR)*T*TPL threads and walks the D components in CR rounds, loading its inputs straight from
+// global memory.  Two such CTAs fit on one SM (registers and shared memory), so the global-load
+// phase of one overlaps the FP64 / shared-memory phases of the other.
+template <int N, int T, int KIND, int DIM, int CR>
+__global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) / CR) * T * FastCfg<N>::TPL, 2)
+    k_mid_green_2r(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh, int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int DC = D / CR;  // components per round
+    constexpr int Ra = FastCfg<N>::R1, Rb = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
+    constexpr int NPR = N + N / 16;
+    constexpr int NT = DC * T * TPL;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [D][NPR][T]
+    const int t = threadIdx.x % T;
+    const int j = (threadIdx.x / T) % TPL;
+    const int c0 = threadIdx.x / (T * TPL);
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    // F1: global -> registers -> smem (digit-reversed rows come out of F2)
+#pragma unroll
+    for (int h = 0; h < CR; ++h) {
+        const int c = c0 + h * DC;
+        if (j < Rb) {
+            cplx v[Ra];
+            const cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+#pragma unroll
+            for (int r = 0; r < Ra; ++r) v[r] = gp[(int64_t)(j + r * Rb) * inner];
+            Bfly<Ra, false>::run(v);
+#pragma unroll
+            for (int q = 1; q < Ra; ++q) v[q] = cmul(v[q], ldtw(tw, q * j, false));
+            cplx* sc = buf + c * NPR * T + t;
+#pragma unroll
+            for (int q = 0; q < Ra; ++q) sc[pidx(j + q * Rb) * T] = v[q];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < CR; ++h) {
+        cplx* sc = buf + (c0 + h * DC) * NPR * T + t;
+        if (j < Ra) {
+            cplx v[Rb];
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) v[s] = sc[pidx(j * Rb + s) * T];
+            Bfly<Rb, false>::run(v);
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) sc[pidx(j * Rb + s) * T] = v[s];
+        }
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < N * T; idx += NT) {
+        const int row = idx / T, tt = idx - row * T;
+        const int q = row / Rb, s = row - q * Rb;
+        int k[3];
+        k[0] = fh_freq(q + Ra * s, N);
+        const int64_t ii = i0 + tt;
+        bool valid = true;
+        if (DIM == 3) {
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            k[1] = fh_freq(i1, g.N[1]);
+            k[2] = fh_freq(i2, g.N[2]);
+            valid = i2 < nh;
+        } else {
+            k[1] = fh_freq((int)ii, g.N[1]);
+            k[2] = 0;
+            valid = (int)ii < nh;
+        }
+        cplx* sr = buf + pidx(row) * T + tt;
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * NPR * T];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) sr[cc * NPR * T] = e[cc];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < CR; ++h) {
+        cplx* sc = buf + (c0 + h * DC) * NPR * T + t;
+        if (j < Ra) {
+            cplx v[Rb];
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) v[s] = sc[pidx(j * Rb + s) * T];
+            Bfly<Rb, true>::run(v);
+#pragma unroll
+            for (int s = 0; s < Rb; ++s) sc[pidx(j * Rb + s) * T] = v[s];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < CR; ++h) {
+        const int c = c0 + h * DC;
+        if (j < Rb) {
+            cplx v[Ra];
+            const cplx* sc = buf + c * NPR * T + t;
+#pragma unroll
+            for (int q = 0; q < Ra; ++q) v[q] = sc[pidx(j + q * Rb) * T];
+#pragma unroll
+            for (int q = 1; q < Ra; ++q) v[q] = cmul(v[q], ldtw(tw, q * j, true));
+            Bfly<Ra, true>::run(v);
+            cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+#pragma unroll
+            for (int r = 0; r < Ra; ++r) gp[(int64_t)(j + r * Rb) * inner] = v[r];
+        }
+    }
+}

@@ -233,11 +233,33 @@ static int launch_mid_pipe_NT(fh_ga* op) {
     return FH_OK;
 }
 
+template <int N, int T, int KIND, int DIM, int CR>
+static int launch_mid_2r_NT(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const fh_plan* p = op->plan;
+    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const size_t smem = (size_t)D * (N + N / 16) * T * sizeof(cplx);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_2r<N, T, KIND, DIM, CR>, smem))) return rc;
+    k_mid_green_2r<N, T, KIND, DIM, CR><<<(unsigned)(inner / T), (D / CR) * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
+        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
 template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
-    if (op->mid_pipe && T == 4) {
+    if (op->mid_pipe == 2 && T == 4) {
+        constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+        constexpr int CR = (D % 2 == 0) ? 2 : (D % 3 == 0 ? 3 : 1);
+        if (env_int("FH_MID_CR1", 0) && N == 256) return launch_mid_2r_NT<256, 4, KIND, DIM, 1>(op);
+        if (N == 64) return launch_mid_2r_NT<64, 4, KIND, DIM, CR>(op);
+        if (N == 128) return launch_mid_2r_NT<128, 4, KIND, DIM, CR>(op);
+        if (N == 256) return launch_mid_2r_NT<256, 4, KIND, DIM, CR>(op);
+    }
+    if (op->mid_pipe == 1 && T == 4) {
         constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
         if ((size_t)2 * D * (N + N / 16) * 4 * sizeof(cplx) <= (size_t)fh_max_smem_optin()) {
             if (N == 64) return launch_mid_pipe_NT<64, 4, KIND, DIM>(op);

@@ -108,3 +108,25 @@ def test_no_product_module_imports_the_oracle():
             if f.endswith('.py'):
                 src = open(os.path.join(dp, f)).read()
                 assert 'oracle' not in src.replace('no CPU oracle', ''), os.path.join(dp, f)
+
+
+def test_install_splices_into_the_reference_tree():
+    """with the unmodified reference importable, install() makes its callers
+    (applications, materials, postprocess, problem) bind the B200 objects.  Skipped where the
+    reference tree is absent (GPU box)."""
+    import subprocess
+    import sys
+    import _refshim
+    if not _refshim.available():
+        pytest.skip('reference tree not present')
+    code = (
+        "import sys; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import _refshim; _refshim.install()\n"
+        "import ffthompy_b200; ffthompy_b200.install()\n"
+        "import ffthompy.applications as apps, ffthompy.materials as M, ffthompy.postprocess, ffthompy.problem\n"
+        "import ffthompy_b200.tensors as T, ffthompy_b200.projections as P\n"
+        "assert apps.Tensor is T.Tensor and M.Tensor is T.Tensor and apps.proj is P\n"
+        "assert apps.linear_solver.__module__ == 'ffthompy_b200.general.solver'\n"
+        "print('spliced')\n") % (os.path.join(ROOT, 'oracle'), ROOT)
+    out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
+    assert out.returncode == 0 and 'spliced' in out.stdout, out.stderr
