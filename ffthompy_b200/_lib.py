@@ -71,6 +71,12 @@ _SIGNATURES = {
     'fh_green4_materialize': (c_int, [c_int, c_int, p_i64, p_dbl, c_int, c_vp]),
     'fh_ga_work_doubles': (c_i64, [c_vp, c_int]),
     'fh_ga_create': (c_int, [C.POINTER(c_vp), c_vp, c_int, c_vp, c_int, C.POINTER(fh_green), c_vp]),
+    'fh_ga_slab_work_doubles': (c_i64, [c_vp, c_int, c_int, c_int]),
+    'fh_ga_create_slab': (c_int, [C.POINTER(c_vp), c_vp, c_int, c_vp, c_int, C.POINTER(fh_green), c_vp, c_int, c_int,
+                                  c_int]),
+    'fh_ga_buffers': (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), p_int]),
+    'fh_cg_xr_update': (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, p_dbl]),
+    'fh_cg_p_update': (c_int, [c_i64, c_vp, c_vp, c_dbl]),
     'fh_ga_destroy': (c_int, [c_vp]),
     'fh_ga_apply': (c_int, [c_vp, c_vp, c_vp]),
     'fh_ga_config': (c_int, [c_vp, p_int, p_int, p_int]),

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
         bool valid = true;
         if (DIM == 3) {
             const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
-            k[1] = fh_freq(i1, g.N[1]);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
             k[2] = fh_freq(i2, g.N[2]);
             valid = i2 < nh;
         } else {
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
             bool valid = true;
             if (DIM == 3) {
                 const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
-                k[1] = fh_freq(i1, g.N[1]);
+                k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
                 k[2] = fh_freq(i2, g.N[2]);
                 valid = i2 < nh;
             } else {
@@ -610,7 +610,7 @@ __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM
         bool valid = true;
         if (DIM == 3) {
             const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
-            k[1] = fh_freq(i1, g.N[1]);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
             k[2] = fh_freq(i2, g.N[2]);
             valid = i2 < nh;
         } else {

@@ -36,7 +36,10 @@ struct fh_ga {
     int nphase;
     GreenDesc g;
     int pitch;       // padded spectrum row length (complex elements)
-    int64_t nrows;   // prod(N[:-1])
+    int64_t nrows;   // rows of the local real fields: prod(N[:-1]), or n0_local*N1 for a slab
+    int64_t nloc;    // local voxels per component = nrows * N_last
+    int n0l, n1l;    // slab decomposition (3-D): local planes of axis 0 (real space) / axis 1 (axis-0 pass)
+    cplx* specT;     // [D][N0][n1l][pitch] y-slab spectrum (== spec when not decomposed)
     int64_t nspecp;  // nrows * pitch
     double* work;
     double* sigma;  // [D*nreal] (generic last-axis path only)
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(GA_NT) k_mid_green(cplx* __restrict__ data, Ax
         bool valid;
         if (DIM == 3) {
             const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
-            k[1] = fh_freq(i1, g.N[1]);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
             k[2] = fh_freq(i2, g.N[2]);
             valid = i2 < nh;
         } else {
@@ -152,7 +155,7 @@ static int launch_mid_green_generic(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     const fh_plan* p = op->plan;
     const AxisDesc& ax = p->ax[0];
-    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     int T = 8;
     while (T > 1 && fft_smem_bytes(ax.n, fft_ld(D * T)) > (size_t)113 * 1024) T >>= 1;
     while (T > 1 && fft_smem_bytes(ax.n, fft_ld(D * T)) > (size_t)fh_max_smem_optin()) T >>= 1;
@@ -163,7 +166,7 @@ static int launch_mid_green_generic(fh_ga* op) {
     if (smem > 48 * 1024)
         FH_CUDA(cudaFuncSetAttribute(k_mid_green<KIND, DIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t nblk = fh_ceil_div(inner, T);
-    k_mid_green<KIND, DIM><<<(unsigned)nblk, GA_NT, smem, fh_stream()>>>(op->spec, ax, op->g, inner, T, ld, p->nh,
+    k_mid_green<KIND, DIM><<<(unsigned)nblk, GA_NT, smem, fh_stream()>>>(op->specT, ax, op->g, inner, T, ld, p->nh,
                                                                           op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
@@ -207,12 +210,12 @@ template <int N, int T, int KIND, int DIM>
 static int launch_mid_fast_NT(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     const fh_plan* p = op->plan;
-    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     const size_t smem = (size_t)D * N * T * sizeof(cplx);
     int rc;
     if ((rc = smem_attr(k_mid_green_fast<N, T, KIND, DIM>, smem))) return rc;
     k_mid_green_fast<N, T, KIND, DIM><<<(unsigned)(inner / T), D * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
-        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
+        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -221,14 +224,14 @@ template <int N, int T, int KIND, int DIM>
 static int launch_mid_pipe_NT(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     const fh_plan* p = op->plan;
-    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     const size_t smem = (size_t)2 * D * (N + N / 16) * T * sizeof(cplx);
     const int ntiles = (int)(inner / T);
     int rc;
     if ((rc = smem_attr(k_mid_green_pipe<N, T, KIND, DIM>, smem))) return rc;
     const int grid = ntiles < fh_num_sms() ? ntiles : fh_num_sms();
     k_mid_green_pipe<N, T, KIND, DIM><<<grid, D * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
-        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch, ntiles);
+        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch, ntiles);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -237,12 +240,12 @@ template <int N, int T, int KIND, int DIM, int CR>
 static int launch_mid_2r_NT(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     const fh_plan* p = op->plan;
-    const int64_t inner = (DIM == 3) ? (int64_t)p->N[1] * op->pitch : op->pitch;
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     const size_t smem = (size_t)D * (N + N / 16) * T * sizeof(cplx);
     int rc;
     if ((rc = smem_attr(k_mid_green_2r<N, T, KIND, DIM, CR>, smem))) return rc;
     k_mid_green_2r<N, T, KIND, DIM, CR><<<(unsigned)(inner / T), (D / CR) * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
-        op->spec, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
+        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -389,7 +392,7 @@ __global__ void k_lut_fetch(int64_t n, int DD, const double* __restrict__ A, int
 #define FH_MAX_PHASES 16
 static int analyse_coefficients(fh_ga* op) {
     const int D = op->D, DD = D * D;
-    const int64_t n = op->plan->nreal;
+    const int64_t n = op->nloc;
     const int want = env_int("FH_AMODE", -1);  // -1 auto, 0 full, 1 sym, 2 phase table
     op->a_mode = 0;
     op->phase = NULL;
@@ -448,16 +451,30 @@ static int analyse_coefficients(fh_ga* op) {
 }
 
 // ------------------------------------------------------------------ operator object
-static int64_t sigma_doubles(const fh_plan* p, int D) { return ((int64_t)D * p->nreal + 15) / 16 * 16; }
 static int pitch_for(const fh_plan* p) { return (p->nh + 7) / 8 * 8; }
+static int64_t round16(int64_t v) { return (v + 15) / 16 * 16; }
+
+// work = [sigma: D*nloc (rounded)] [spec: D*n0l*N1*pitch complex] [specT: D*N0*n1l*pitch complex, slabs only]
+static int64_t work_doubles(const fh_plan* p, int D, int n0l, int n1l) {
+    const int d = p->dim;
+    const int64_t rows_other = (d == 3) ? p->N[1] : 1;
+    const int64_t nloc = (int64_t)n0l * rows_other * p->N[d - 1];
+    int64_t w = round16((int64_t)D * nloc) + 2 * (int64_t)D * n0l * rows_other * pitch_for(p);
+    if (d == 3 && (n0l != p->N[0] || n1l != p->N[1])) w += 2 * (int64_t)D * p->N[0] * n1l * pitch_for(p);
+    return w;
+}
 
 extern "C" int64_t fh_ga_work_doubles(const fh_plan* p, int D) {
     if (!p || D < 1) return 0;
-    return sigma_doubles(p, D) + 2 * (int64_t)D * (p->nreal / p->N[p->dim - 1]) * pitch_for(p);
+    return work_doubles(p, D, p->N[0], p->dim == 3 ? p->N[1] : 1);
+}
+extern "C" int64_t fh_ga_slab_work_doubles(const fh_plan* p, int D, int n0_local, int n1_local) {
+    if (!p || D < 1 || p->dim != 3) return 0;
+    return work_doubles(p, D, n0_local, n1_local);
 }
 
-extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
-                            double* work) {
+static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
+                     double* work, int n0l, int n1l, int n1_off) {
     FH_REQUIRE(out && plan && A && g && work, "fh_ga_create: null argument");
     FH_REQUIRE(plan->dim == 2 || plan->dim == 3, "fh_ga_create: dim must be 2 or 3");
     FH_REQUIRE(a_layout == 0, "fh_ga_create: unsupported coefficient layout %d", a_layout);
@@ -466,6 +483,10 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     FH_REQUIRE(D == Dexp, "fh_ga_create: D=%d does not match Green kind %d in dim %d", D, g->kind, plan->dim);
     for (int a = 0; a < plan->dim; ++a)
         FH_REQUIRE(g->N[a] == plan->N[a], "fh_ga_create: Green descriptor grid differs from the plan grid");
+    const int d = plan->dim;
+    const bool slab = (d == 3) && (n0l != plan->N[0] || n1l != plan->N[1]);
+    FH_REQUIRE(n0l >= 1 && n0l <= plan->N[0] && n1l >= 1 && n1_off >= 0 && (d == 2 || n1_off + n1l <= plan->N[1]),
+               "fh_ga_create: bad slab extents");
     fh_ga* op = (fh_ga*)calloc(1, sizeof(fh_ga));
     if (!op) return fh_set_error(FH_ERR_ALLOC, "fh_ga_create: out of host memory");
     int rc = fh_fill_green(op->g, g);
@@ -473,23 +494,27 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
         free(op);
         return rc;
     }
+    op->g.ioff1 = n1_off;
     op->plan = plan;
     op->D = D;
     op->A = A;
     op->a_layout = a_layout;
     op->pitch = pitch_for(plan);
-    op->nrows = plan->nreal / plan->N[plan->dim - 1];
+    op->n0l = n0l;
+    op->n1l = (d == 3) ? n1l : 1;
+    op->nrows = (d == 3) ? (int64_t)n0l * plan->N[1] : n0l;
+    op->nloc = op->nrows * plan->N[d - 1];
     op->nspecp = op->nrows * op->pitch;
     op->work = work;
     op->sigma = work;
-    op->spec = (cplx*)(work + sigma_doubles(plan, D));
+    op->spec = (cplx*)(work + round16((int64_t)D * op->nloc));
+    op->specT = slab ? op->spec + (size_t)D * op->nspecp : op->spec;
     const int use_fast = env_int("FH_FAST", 1);
-    const int d = plan->dim;
     op->trw = trw_for(D);
     if (D == 6 && env_int("FH_TRW", 4) == 2) op->trw = 2;
     op->fast_last = use_fast && fh_fast_len(plan->N[d - 1]) && (op->nrows % op->trw == 0);
     op->fast_mid1 = use_fast && d == 3 && fh_fast_len(plan->N[1]);
-    op->fast_mid0 = use_fast && fh_fast_len(plan->N[0]);
+    op->fast_mid0 = use_fast && fh_fast_len(plan->N[0]) && (((int64_t)op->n1l * op->pitch) % 4 == 0);
     op->mid_T = env_int("FH_MID_T", 4);
     op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
@@ -499,6 +524,8 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
     if (e == cudaSuccess) e = cudaMemset(op->scal, 0, sizeof(double) * (16 + GA_MAXPART));
     // padding columns of the spectrum rows are never read as data; zero them once for determinism
     if (e == cudaSuccess) e = cudaMemset(op->spec, 0, sizeof(cplx) * D * op->nspecp);
+    if (e == cudaSuccess && slab)
+        e = cudaMemset(op->specT, 0, sizeof(cplx) * D * (size_t)plan->N[0] * op->n1l * op->pitch);
     if (e != cudaSuccess) {
         free(op);
         return fh_set_error(FH_ERR_CUDA, "fh_ga_create: %s", cudaGetErrorString(e));
@@ -509,6 +536,32 @@ extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const doubl
         return rc;
     }
     *out = op;
+    return FH_OK;
+}
+
+extern "C" int fh_ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
+                            double* work) {
+    FH_REQUIRE(plan, "fh_ga_create: null plan");
+    return ga_create(out, plan, D, A, a_layout, g, work, plan->N[0], plan->dim == 3 ? plan->N[1] : 1, 0);
+}
+
+// Slab-decomposed operator of one rank (3-D): real-space fields hold n0_local planes of axis 0
+// (A, x, y are the LOCAL arrays [.][n0_local][N1][N2]); the axis-0 pass (S3) runs on the transposed
+// spectrum [D][N0][n1_local][pitch] holding the global axis-1 indices [n1_offset, n1_offset+n1_local).
+// The caller moves the spectrum between the two layouts (all-to-all) between S2/S3 and S3/S4 and
+// reduces the CG scalars across ranks; see ffthompy_b200/slab.py.
+extern "C" int fh_ga_create_slab(fh_ga** out, const fh_plan* plan, int D, const double* A_local, int a_layout,
+                                 const fh_green* g, double* work, int n0_local, int n1_local, int n1_offset) {
+    FH_REQUIRE(plan && plan->dim == 3, "fh_ga_create_slab: a 3-D plan is required");
+    return ga_create(out, plan, D, A_local, a_layout, g, work, n0_local, n1_local, n1_offset);
+}
+
+// device pointers of the two spectrum layouts (x-slab [D][n0l][N1][pitch], y-slab [D][N0][n1l][pitch])
+extern "C" int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch) {
+    FH_REQUIRE(op, "fh_ga_buffers: null argument");
+    if (spec) *spec = op->spec;
+    if (specT) *specT = op->specT;
+    if (pitch) *pitch = op->pitch;
     return FH_OK;
 }
 
@@ -663,7 +716,7 @@ __global__ void k_rich_update(int64_t n, double* __restrict__ x, const double* _
 static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdate, double* y, int dot, int* npart) {
     const fh_plan* p = op->plan;
     const int D = op->D, d = p->dim;
-    const int64_t n = p->nreal;
+    const int64_t n = op->nloc;  // local voxels per component
     const int64_t nlines = (int64_t)D * op->nrows;
     int rc;
     switch (stage) {
@@ -683,8 +736,8 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
             return fh_launch_r2c_last(p, op->sigma, op->spec, nlines, op->pitch);
         case 2:
             if (d != 3) return FH_OK;
-            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * p->N[0], op->pitch, false);
-            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], op->pitch, false, 1.0);
+            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, false);
+            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, false, 1.0);
         case 3:
             if (op->fast_mid0) {
                 if (op->g.kind == FH_GREEN_SCALAR)
@@ -698,11 +751,11 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
                             : launch_mid_green_generic<FH_GREEN_ELASTIC, 2>(op);
         case 4:
             if (d != 3) return FH_OK;
-            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * p->N[0], op->pitch, true);
-            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * p->N[0], op->pitch, true, 1.0);
+            if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, true);
+            return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, true, 1.0);
         case 5:
             if (op->fast_last) return launch_inv_last_fast(op, y, dot ? x : NULL, npart);
-            if ((rc = fh_launch_c2r_last(p, op->spec, y, nlines, op->pitch, 1.0 / (double)n))) return rc;
+            if ((rc = fh_launch_c2r_last(p, op->spec, y, nlines, op->pitch, 1.0 / (double)p->nreal))) return rc;
             if (dot) {
                 const unsigned g = ga_grid(D * n);
                 k_dot_part<<<g, GA_NT, 0, fh_stream()>>>(D * n, x, y, op->part);
@@ -745,7 +798,7 @@ static int read_norm(fh_ga* op, double* out) {
 // fh_cg_begin: Ax = Afun(x0); R = B - Ax; P = R; rr = <R,R>      (solver.py:113-120)
 extern "C" int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, double* norm_res_host) {
     FH_REQUIRE(op && B && x && vecs && norm_res_host, "fh_cg_begin: null argument");
-    const int64_t n = (int64_t)op->D * op->plan->nreal;
+    const int64_t n = (int64_t)op->D * op->nloc;
     const double inv = 1.0 / (double)op->plan->nreal;
     double* r = vecs;
     double* p = vecs + n;
@@ -768,7 +821,7 @@ extern "C" int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, 
 extern "C" int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
                            double* norm_res_host, double* hist_host) {
     FH_REQUIRE(op && x && vecs && done_host && norm_res_host, "fh_cg_steps: null argument");
-    const int64_t n = (int64_t)op->D * op->plan->nreal;
+    const int64_t n = (int64_t)op->D * op->nloc;
     const double inv = 1.0 / (double)op->plan->nreal;
     double* r = vecs;
     double* p = vecs + n;
@@ -827,7 +880,7 @@ extern "C" int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t 
 extern "C" int fh_richardson(fh_ga* op, const double* B, double* x, double alpha, double tol, int64_t maxiter,
                              double* vecs, int64_t* kit_host, double* norm_res_host) {
     FH_REQUIRE(op && B && x && vecs && kit_host && norm_res_host, "fh_richardson: null argument");
-    const int64_t n = (int64_t)op->D * op->plan->nreal;
+    const int64_t n = (int64_t)op->D * op->nloc;
     const double inv = 1.0 / (double)op->plan->nreal;
     const double omega = 1.0 / alpha;
     double* Ax = vecs;

@@ -34,6 +34,7 @@ struct GreenDesc {
     double Y[3];
     double c0, cI, cS, cH, cL, cW;
     double scale;
+    int ioff1;  // added to the axis-1 storage index (slab-decomposed spectra: this rank owns k1 in [ioff1, ioff1+n1l))
 };
 
 // e: D complex components (in place).  k: signed integer frequencies.

@@ -915,6 +915,7 @@ static int fill_green(GreenDesc& g, const fh_green* in) {
     g.cL = in->cL;
     g.cW = in->cW;
     g.scale = in->scale;
+    g.ioff1 = 0;
     return FH_OK;
 }
 int fh_fill_green(GreenDesc& g, const fh_green* in) { return fill_green(g, in); }
@@ -1007,6 +1008,51 @@ extern "C" int fh_green4_materialize(int kind, int dim, const int64_t* N, const 
     const int64_t nf = freq_count(f);
     if (nf == 0) return FH_OK;
     k_green4<<<grid_for(nf), FH_NT, 0, fh_stream()>>>(f, nf, kind, out);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
+// ------------------------------------------------------------------ CG vector updates as stand-alone calls
+// (used by the slab-decomposed loop, where the scalars are reduced across ranks by the caller)
+// x += alpha p ; r -= alpha Ap ; *rr_local = sum r.r over this rank's entries   (solver.py:127-129)
+__global__ void k_xr_update(int64_t n, double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p,
+                            const double* __restrict__ Ap, double alpha, double* __restrict__ part) {
+    __shared__ double red[32];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        x[i] = x[i] + alpha * p[i];
+        const double v = r[i] - alpha * Ap[i];
+        r[i] = v;
+        acc += v * v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+extern "C" int fh_cg_xr_update(int64_t n, double* x, double* r, const double* p, const double* Ap, double alpha,
+                               double* rr_local_host) {
+    FH_REQUIRE(n >= 0 && x && r && p && Ap && rr_local_host, "fh_cg_xr_update: bad argument");
+    int rc;
+    if ((rc = ensure_scratch())) return rc;
+    if (n == 0) {
+        *rr_local_host = 0.0;
+        return FH_OK;
+    }
+    unsigned g = grid_for(n, 8);
+    if (g > FH_RED_MAX) g = FH_RED_MAX;
+    k_xr_update<<<g, FH_NT, 0, fh_stream()>>>(n, x, r, p, Ap, alpha, g_red_dev);
+    FH_LAUNCH_CHECK();
+    return finish_reduction((int)g, 1, 0, rr_local_host);
+}
+// p = r + beta p   (solver.py:132)
+__global__ void k_p_update(int64_t n, double* __restrict__ p, const double* __restrict__ r, double beta) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = r[i] + beta * p[i];
+}
+extern "C" int fh_cg_p_update(int64_t n, double* p, const double* r, double beta) {
+    FH_REQUIRE(n >= 0 && p && r, "fh_cg_p_update: bad argument");
+    if (n == 0) return FH_OK;
+    k_p_update<<<grid_for(n, 4), FH_NT, 0, fh_stream()>>>(n, p, r, beta);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }

@@ -125,6 +125,13 @@ int fh_green4_materialize(int kind, int dim, const int64_t* N, const double* Y, 
 int64_t fh_ga_work_doubles(const fh_plan* plan, int D);
 int fh_ga_create(fh_ga** op, const fh_plan* plan, int D, const double* A, int a_layout, const fh_green* g,
                  double* work);
+/* slab-decomposed operator of one rank (3-D): local real fields [.][n0_local][N1][N2];
+ * S3 runs on the transposed spectrum [D][N0][n1_local][pitch] with global axis-1 offset n1_offset;
+ * the caller exchanges the spectrum between the two layouts (fh_ga_buffers) around S3 */
+int64_t fh_ga_slab_work_doubles(const fh_plan* plan, int D, int n0_local, int n1_local);
+int fh_ga_create_slab(fh_ga** op, const fh_plan* plan, int D, const double* A_local, int a_layout, const fh_green* g,
+                      double* work, int n0_local, int n1_local, int n1_offset);
+int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch);
 int fh_ga_destroy(fh_ga* op);
 int fh_ga_apply(fh_ga* op, const double* x, double* y);
 /* flags: bit0/1/2 = register-resident power-of-two kernels on the last axis / axis 1 / axis 0 */
@@ -144,6 +151,10 @@ int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, 
 /* vecs: 2*D*prod(N) doubles */
 int fh_richardson(fh_ga* op, const double* B, double* x, double alpha, double tol, int64_t maxiter, double* vecs,
                   int64_t* kit_host, double* norm_res_host);
+/* stand-alone CG vector updates (slab loop: scalars are reduced across ranks by the caller) */
+int fh_cg_xr_update(int64_t n, double* x, double* r, const double* p, const double* Ap, double alpha,
+                    double* rr_local_host);
+int fh_cg_p_update(int64_t n, double* p, const double* r, double beta);
 /* kernels launched by this library since fh_init (for bench.py's gpu_launches) */
 int64_t fh_launch_count(void);
 
