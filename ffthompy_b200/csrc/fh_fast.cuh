@@ -54,14 +54,14 @@ __device__ __forceinline__ cplx ldtw(const cplx* __restrict__ tw, int i, bool in
 template <int N, int T, bool INV>
 __global__ void __launch_bounds__(T* FastCfg<N>::TPL) k_c2c_fast(const cplx* __restrict__ in, cplx* __restrict__ out,
                                                                   const cplx* __restrict__ tw, int64_t inner,
-                                                                  int ntile, double scale) {
+                                                                  int ntile, int tile0, double scale) {
     constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [N][T]
     const int t = threadIdx.x % T, j = threadIdx.x / T;
     const int64_t o = blockIdx.x / ntile;
     const int tile = blockIdx.x - (int)(o * ntile);
-    const int64_t base = o * N * inner + (int64_t)tile * T + t;
+    const int64_t base = o * N * inner + (int64_t)(tile0 + tile) * T + t;  // tile0: first tile of a column chunk
     if (j < R2) {
         cplx v[R1];
 #pragma unroll
@@ -188,10 +188,17 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 //   memory (detected by fh_ga_create, e.g. inclusion-type microstructures);  -1: no multiply
 __device__ __forceinline__ int pidx(int row) { return row + (row >> 4); }
 
+// two-phase coefficient table passed BY VALUE (kernel parameter = constant bank): both matrices
+// are read with uniform addresses and selected per voxel, so the per-voxel gather costs no shared
+// memory bandwidth (A layout 3)
+struct Lut2C {
+    double c[2][36];
+};
+
 template <int N, int D, int TRW, int ALAY>
 __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     k_fwd_last_fast(const double* __restrict__ A, const unsigned char* __restrict__ phase,
-                    const double* __restrict__ lut, int nphase, double* __restrict__ p,
+                    const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
                     const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
                     cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
     constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
@@ -214,10 +221,10 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
         const int row = v / (N / 2), i2 = 2 * (v - row * (N / 2));
         const int64_t gv = (row0 + row) * N + i2;
         int ph0 = 0, ph1 = 0;
-        if (ALAY == 2) {
+        if (ALAY == 2 || ALAY == 3) {
             const uchar2 ph = *reinterpret_cast<const uchar2*>(phase + gv);
-            ph0 = ph.x * D * D;
-            ph1 = ph.y * D * D;
+            ph0 = (ALAY == 2) ? ph.x * D * D : ph.x;
+            ph1 = (ALAY == 2) ? ph.y * D * D : ph.y;
         }
         double2 pv[D];
 #pragma unroll
@@ -240,7 +247,10 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
 #pragma unroll
                 for (int jj = 0; jj < D; ++jj) {
                     double2 a;
-                    if (ALAY == 2) {
+                    if (ALAY == 3) {
+                        const double c0 = lutc.c[0][i * D + jj], c1 = lutc.c[1][i * D + jj];
+                        a = make_double2(ph0 ? c1 : c0, ph1 ? c1 : c0);
+                    } else if (ALAY == 2) {
                         a = make_double2(slut[ph0 + i * D + jj], slut[ph1 + i * D + jj]);
                     } else if (ALAY == 1) {  // symmetric: (i,j) and (j,i) read the same upper-triangle entry
                         const int lo = i < jj ? i : jj, hi = i < jj ? jj : i;
@@ -429,6 +439,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+// named barrier over `nthreads` consecutive threads (a multiple of 32); id 0 is __syncthreads
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;\n" ::"r"(id), "r"(nthreads) : "memory");
+}
 template <int NG>
 __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(NG));
@@ -437,7 +451,7 @@ __device__ __forceinline__ void cp_async_wait() {
 template <int N, int T, int KIND, int DIM>
 __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) * T * FastCfg<N>::TPL, 1)
     k_mid_green_pipe(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
-                     int pitch, int ntiles) {
+                     int pitch, int ntiles, int tpr, int col0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int Ra = FastCfg<N>::R1, Rb = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
     constexpr int NPR = N + N / 16;        // padded rows per component
@@ -449,8 +463,14 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
     const int j = (threadIdx.x / T) % TPL;
     const int c = threadIdx.x / (T * TPL);
 
+    // tile -> first inner index: tiles walk `tpr` tiles per spectrum row starting at column col0
+    // (whole rows: tpr = pitch/T, col0 = 0; a column chunk for L2 blocking: tpr = chunk/T)
+    auto tile_i0 = [&](int tile) -> int64_t {
+        const int rowi = tile / tpr;
+        return (int64_t)rowi * pitch + col0 + (tile - rowi * tpr) * T;
+    };
     auto prefetch = [&](int tile, cplx* buf) {
-        const int64_t i0 = (int64_t)tile * T;
+        const int64_t i0 = tile_i0(tile);
 #pragma unroll 4
         for (int e = threadIdx.x; e < D * N * T; e += NT) {
             const int tt = e % T, row = (e / T) % N, cc = e / (T * N);
@@ -469,7 +489,7 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
         cp_async_wait<1>();
         __syncthreads();
         cplx* sc = cur + c * NPR * T + t;
-        const int64_t i0 = (int64_t)tile * T;
+        const int64_t i0 = tile_i0(tile);
         // F1
         if (j < Rb) {
             cplx v[Ra];
@@ -481,7 +501,7 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 #pragma unroll
             for (int q = 0; q < Ra; ++q) sc[pidx(j + q * Rb) * T] = v[q];
         }
-        __syncthreads();
+        group_sync(c + 1, T * TPL);  // F2 of component c only needs the F1 output of the same T*TPL threads
         // F2
         if (j < Ra) {
             cplx v[Rb];
@@ -533,7 +553,7 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 #pragma unroll
             for (int s = 0; s < Rb; ++s) sc[pidx(j * Rb + s) * T] = v[s];
         }
-        __syncthreads();
+        group_sync(c + 1, T * TPL);
         // I1 -> global
         if (j < Rb) {
             cplx v[Ra];
@@ -551,6 +571,29 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
     cp_async_wait<0>();
 }
 
+// debugging aid: pure data movement of the axis-0 tiling (global -> smem -> global), to measure what
+// the access pattern alone achieves
+template <int N, int T, int D>
+__global__ void __launch_bounds__(D * T * 16) k_mid_copy_only(cplx* __restrict__ data, int64_t inner) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int t = threadIdx.x % T;
+    const int j = (threadIdx.x / T) % 16;
+    const int c = threadIdx.x / (T * 16);
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+    cplx v[N / 16];
+#pragma unroll
+    for (int r = 0; r < N / 16; ++r) v[r] = gp[(int64_t)(j + r * 16) * inner];
+#pragma unroll
+    for (int r = 0; r < N / 16; ++r) buf[(c * N + j + r * 16) * T + t] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < N / 16; ++r) v[r] = buf[(c * N + j * (N / 16) + r) * T + t];
+#pragma unroll
+    for (int r = 0; r < N / 16; ++r) gp[(int64_t)(j + r * 16) * inner] = v[r];
+}
+
 // ------------------------------------------------------------------ axis 0 + G^, two CTAs per SM
 // Same in-place DIF / mirrored-inverse scheme as k_mid_green_pipe, but each CTA has only
 // (D/CR)*T*TPL threads and walks the D components in CR rounds, loading its inputs straight from
@@ -558,7 +601,8 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 // phase of one overlaps the FP64 / shared-memory phases of the other.
 template <int N, int T, int KIND, int DIM, int CR>
 __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) / CR) * T * FastCfg<N>::TPL, 2)
-    k_mid_green_2r(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh, int pitch) {
+    k_mid_green_2r(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh, int pitch,
+                   int tpr, int col0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int DC = D / CR;  // components per round
     constexpr int Ra = FastCfg<N>::R1, Rb = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
@@ -569,7 +613,8 @@ __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM
     const int t = threadIdx.x % T;
     const int j = (threadIdx.x / T) % TPL;
     const int c0 = threadIdx.x / (T * TPL);
-    const int64_t i0 = (int64_t)blockIdx.x * T;
+    const int rowi = blockIdx.x / tpr;
+    const int64_t i0 = (int64_t)rowi * pitch + col0 + (blockIdx.x - rowi * tpr) * T;
     // F1: global -> registers -> smem (digit-reversed rows come out of F2)
 #pragma unroll
     for (int h = 0; h < CR; ++h) {
@@ -601,12 +646,11 @@ __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM
         }
     }
     __syncthreads();
-    for (int idx = threadIdx.x; idx < N * T; idx += NT) {
-        const int row = idx / T, tt = idx - row * T;
-        const int q = row / Rb, s = row - q * Rb;
-        int k[3];
-        k[0] = fh_freq(q + Ra * s, N);
+    {
+        // NT is a multiple of T: the tile column (hence k1, k2) is fixed per thread, only k0 varies
+        const int tt = threadIdx.x % T;
         const int64_t ii = i0 + tt;
+        int k[3];
         bool valid = true;
         if (DIM == 3) {
             const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
@@ -618,18 +662,22 @@ __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM
             k[2] = 0;
             valid = (int)ii < nh;
         }
-        cplx* sr = buf + pidx(row) * T + tt;
-        cplx e[D];
+        for (int row = threadIdx.x / T; row < N; row += NT / T) {
+            const int q = row / Rb, s = row - q * Rb;
+            k[0] = fh_freq(q + Ra * s, N);
+            cplx* sr = buf + pidx(row) * T + tt;
+            cplx e[D];
 #pragma unroll
-        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * NPR * T];
-        if (valid) {
-            green_apply<KIND, DIM>(g, k, e);
-        } else {
+            for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * NPR * T];
+            if (valid) {
+                green_apply<KIND, DIM>(g, k, e);
+            } else {
 #pragma unroll
-            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+                for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) sr[cc * NPR * T] = e[cc];
         }
-#pragma unroll
-        for (int cc = 0; cc < D; ++cc) sr[cc * NPR * T] = e[cc];
     }
     __syncthreads();
 #pragma unroll

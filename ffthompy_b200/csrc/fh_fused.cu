@@ -19,6 +19,7 @@
 #include "fh_fast.cuh"
 #include "../../include/ffthom_b200.h"
 #include <stdlib.h>
+#include <string.h>
 
 int fh_fill_green(GreenDesc& g, const fh_green* in);
 
@@ -33,6 +34,7 @@ struct fh_ga {
     int a_mode;            // how S1 reads the coefficients: 0 full, 1 symmetric (upper triangle), 2 phase table
     unsigned char* phase;  // [prod(N)] phase index per voxel (a_mode 2), owned by the operator
     double* lut;           // [nphase][D][D]
+    Lut2C lutc;            // host copy of the table when nphase <= 2 (passed by value to S1)
     int nphase;
     GreenDesc g;
     int pitch;       // padded spectrum row length (complex elements)
@@ -47,6 +49,8 @@ struct fh_ga {
     // configuration
     bool fast_last, fast_mid1, fast_mid0;
     int mid_T, trw, mid_pipe;
+    int chunk_cols;      // L2 blocking of S2-S3-S4: columns of the spectrum rows per chunk (0 = off)
+    int cur_col0, cur_ncols;  // chunk the next S3 launch works on (0,0 = whole rows)
     // device scalars / partial sums of the Krylov loops
     double* scal;  // [16]: rr, pAp, alpha, beta, norm_res
     double* part;  // [GA_MAXPART]
@@ -179,29 +183,33 @@ static int smem_attr(K kernel, size_t bytes) {
     return FH_OK;
 }
 
+// col0/ncols: column chunk of the spectrum rows (L2 blocking); ncols = 0 means whole rows
 template <int N, int T>
-static int launch_c2c_fast_NT(const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, double scale) {
+static int launch_c2c_fast_NT(const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, double scale,
+                              int col0, int ncols) {
     const size_t smem = (size_t)N * T * sizeof(cplx);
-    const int ntile = (int)(inner / T);
+    const int ntile = ncols ? ncols / T : (int)(inner / T);
+    const int tile0 = col0 / T;
     const unsigned nblk = (unsigned)(outer * ntile);
     const int nt = T * FastCfg<N>::TPL;
     int rc;
     if (inv) {
         if ((rc = smem_attr(k_c2c_fast<N, T, true>, smem))) return rc;
-        k_c2c_fast<N, T, true><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, scale);
+        k_c2c_fast<N, T, true><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, tile0, scale);
     } else {
         if ((rc = smem_attr(k_c2c_fast<N, T, false>, smem))) return rc;
-        k_c2c_fast<N, T, false><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, scale);
+        k_c2c_fast<N, T, false><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, tile0, scale);
     }
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
 
-static int launch_c2c_fast(int N, const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv) {
+static int launch_c2c_fast(int N, const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, int col0 = 0,
+                           int ncols = 0) {
     switch (N) {
-        case 64: return launch_c2c_fast_NT<64, 8>(tw, data, outer, inner, inv, 1.0);
-        case 128: return launch_c2c_fast_NT<128, 8>(tw, data, outer, inner, inv, 1.0);
-        case 256: return launch_c2c_fast_NT<256, 8>(tw, data, outer, inner, inv, 1.0);
+        case 64: return launch_c2c_fast_NT<64, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
+        case 128: return launch_c2c_fast_NT<128, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
+        case 256: return launch_c2c_fast_NT<256, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
     }
     return fh_set_error(FH_ERR_UNSUPPORTED, "no fast strided kernel for N=%d", N);
 }
@@ -226,12 +234,14 @@ static int launch_mid_pipe_NT(fh_ga* op) {
     const fh_plan* p = op->plan;
     const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     const size_t smem = (size_t)2 * D * (N + N / 16) * T * sizeof(cplx);
-    const int ntiles = (int)(inner / T);
+    const int tpr = (op->cur_ncols ? op->cur_ncols : op->pitch) / T;
+    const int nrow = (DIM == 3) ? op->n1l : 1;
+    const int ntiles = nrow * tpr;
     int rc;
     if ((rc = smem_attr(k_mid_green_pipe<N, T, KIND, DIM>, smem))) return rc;
     const int grid = ntiles < fh_num_sms() ? ntiles : fh_num_sms();
     k_mid_green_pipe<N, T, KIND, DIM><<<grid, D * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
-        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch, ntiles);
+        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch, ntiles, tpr, op->cur_col0);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -242,10 +252,12 @@ static int launch_mid_2r_NT(fh_ga* op) {
     const fh_plan* p = op->plan;
     const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
     const size_t smem = (size_t)D * (N + N / 16) * T * sizeof(cplx);
+    const int tpr = (op->cur_ncols ? op->cur_ncols : op->pitch) / T;
+    const int nrow = (DIM == 3) ? op->n1l : 1;
     int rc;
     if ((rc = smem_attr(k_mid_green_2r<N, T, KIND, DIM, CR>, smem))) return rc;
-    k_mid_green_2r<N, T, KIND, DIM, CR><<<(unsigned)(inner / T), (D / CR) * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
-        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch);
+    k_mid_green_2r<N, T, KIND, DIM, CR><<<(unsigned)(nrow * tpr), (D / CR) * T * FastCfg<N>::TPL, smem, fh_stream()>>>(
+        op->specT, p->ax[0].tw, op->g, inner, p->nh, op->pitch, tpr, op->cur_col0);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -254,6 +266,17 @@ template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
+    if (op->mid_pipe == 9 && N == 256) {  // debugging: data movement only
+        constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+        const fh_plan* p = op->plan;
+        const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
+        const size_t smem = (size_t)D * 256 * 4 * sizeof(cplx);
+        int rc;
+        if ((rc = smem_attr(k_mid_copy_only<256, 4, D>, smem))) return rc;
+        k_mid_copy_only<256, 4, D><<<(unsigned)(inner / 4), D * 4 * 16, smem, fh_stream()>>>(op->specT, inner);
+        FH_LAUNCH_CHECK();
+        return FH_OK;
+    }
     if (op->mid_pipe == 2 && T == 4) {
         constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
         constexpr int CR = (D % 2 == 0) ? 2 : (D % 3 == 0 ? 3 : 1);
@@ -291,7 +314,7 @@ static int launch_fwd_last_NTA(fh_ga* op, double* p, const double* r, int pupdat
     const fh_plan* pl = op->plan;
     int rc;
     if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, ALAY>, smem))) return rc;
-    k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->nphase, p, r,
+    k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p, r,
                                                                        op->scal, pupdate, op->spec,
                                                                        pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
                                                                        op->pitch);
@@ -302,6 +325,7 @@ static int launch_fwd_last_NTA(fh_ga* op, double* p, const double* r, int pupdat
 template <int N, int D, int TRW>
 static int launch_fwd_last_NT(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
     if (!withA) return launch_fwd_last_NTA<N, D, TRW, -1>(op, p, r, pupdate);
+    if (op->a_mode == 2 && op->nphase <= 2 && D * D <= 36) return launch_fwd_last_NTA<N, D, TRW, 3>(op, p, r, pupdate);
     if (op->a_mode == 2) return launch_fwd_last_NTA<N, D, TRW, 2>(op, p, r, pupdate);
     if (op->a_mode == 1) return launch_fwd_last_NTA<N, D, TRW, 1>(op, p, r, pupdate);
     return launch_fwd_last_NTA<N, D, TRW, 0>(op, p, r, pupdate);
@@ -428,6 +452,11 @@ static int analyse_coefficients(fh_ga* op) {
         if (ok) {
             op->a_mode = 2;
             op->nphase = nph;
+            memset(&op->lutc, 0, sizeof(op->lutc));
+            if (nph <= 2 && DD <= 36)
+                FH_CUDA(cudaMemcpy(&op->lutc.c[0][0], op->lut, sizeof(double) * DD, cudaMemcpyDeviceToHost));
+            if (nph == 2 && DD <= 36)
+                FH_CUDA(cudaMemcpy(&op->lutc.c[1][0], op->lut + DD, sizeof(double) * DD, cudaMemcpyDeviceToHost));
             return FH_OK;
         }
         cudaFree(op->phase);
@@ -518,6 +547,12 @@ static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, i
     op->mid_T = env_int("FH_MID_T", 4);
     op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
+    // L2 blocking (3-D, all-fast, not slab-decomposed): chunk = FH_CHUNK columns (default 8 = one S2 tile)
+    op->chunk_cols = 0;
+    if (d == 3 && !slab && op->fast_mid0 && op->fast_mid1 && op->mid_T == 4 && op->mid_pipe != 0 && op->mid_pipe != 9) {
+        int cc = env_int("FH_CHUNK", 0);  // off by default: measured slower than whole-row launches
+        if (cc > 0 && cc % 8 == 0 && cc < op->pitch) op->chunk_cols = cc;
+    }
     if ((size_t)D * plan->N[0] * op->mid_T * sizeof(cplx) > (size_t)fh_max_smem_optin()) op->mid_T = 2;
     cudaError_t e = cudaMalloc((void**)&op->scal, sizeof(double) * (16 + GA_MAXPART));
     if (e == cudaSuccess) e = cudaMallocHost((void**)&op->pinned, sizeof(double) * 16);
@@ -767,8 +802,35 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
     return fh_set_error(FH_ERR_ARG, "fused operator: bad stage %d", stage);
 }
 
+// S2-S3-S4 over column chunks of the spectrum rows: each chunk (D*N0*N1*chunk_cols*16 B, ~50 MB at
+// 256^3 elasticity) is transformed along axis 1, axis 0 (+G^) and back while it is resident in the
+// 126 MB L2, so the three stages cost one HBM read and one HBM write of the spectrum instead of three.
+static int ga_mid_chunked(fh_ga* op) {
+    const fh_plan* p = op->plan;
+    const int D = op->D;
+    int rc = FH_OK;
+    for (int c0 = 0; c0 < op->pitch && !rc; c0 += op->chunk_cols) {
+        const int nc = (op->pitch - c0 < op->chunk_cols) ? op->pitch - c0 : op->chunk_cols;
+        op->cur_col0 = c0;
+        op->cur_ncols = nc;
+        rc = launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, false, c0, nc);
+        if (!rc)
+            rc = (op->g.kind == FH_GREEN_SCALAR) ? launch_mid_fast<FH_GREEN_SCALAR, 3>(op)
+                                                 : launch_mid_fast<FH_GREEN_ELASTIC, 3>(op);
+        if (!rc) rc = launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, true, c0, nc);
+    }
+    op->cur_col0 = 0;
+    op->cur_ncols = 0;
+    return rc;
+}
+
 static int ga_matvec(fh_ga* op, double* x, const double* r, int pupdate, double* y, int dot, int* npart) {
     int rc;
+    if (op->chunk_cols > 0) {
+        if ((rc = ga_stage(op, 1, x, r, pupdate, y, dot, npart))) return rc;
+        if ((rc = ga_mid_chunked(op))) return rc;
+        return ga_stage(op, 5, x, r, pupdate, y, dot, npart);
+    }
     for (int s = 1; s <= 5; ++s)
         if ((rc = ga_stage(op, s, x, r, pupdate, y, dot, npart))) return rc;
     return FH_OK;
@@ -783,6 +845,7 @@ extern "C" int fh_ga_apply(fh_ga* op, const double* x, double* y) {
 // workspace carries the state between stages.
 extern "C" int fh_ga_stage(fh_ga* op, int stage, const double* x, double* y) {
     FH_REQUIRE(op && x && y, "fh_ga_stage: null argument");
+    if (stage == 6) return op->chunk_cols > 0 ? ga_mid_chunked(op) : fh_set_error(FH_ERR_ARG, "stage 6: L2 blocking is off");
     int np = 0;
     return ga_stage(op, stage, (double*)x, NULL, 0, y, 1, &np);
 }

@@ -32,6 +32,7 @@ struct GreenDesc {
     int N[3];     // grid the multiplier lives on
     int band[3];  // active iff |k_i| <= band[i] for all i
     double Y[3];
+    double invY[3];  // 1/Y (host-computed): xi = k * invY, no fp64 division per frequency
     double c0, cI, cS, cH, cL, cW;
     double scale;
     int ioff1;  // added to the axis-1 storage index (slab-decomposed spectra: this rank owns k1 in [ioff1, ioff1+n1l))
@@ -45,7 +46,7 @@ __device__ __forceinline__ void green_scalar(const GreenDesc& g, const int* k, c
     bool inband = true;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
-        xi[i] = (double)k[i] / g.Y[i];
+        xi[i] = (double)k[i] * g.invY[i];
         s += xi[i] * xi[i];
         inband = inband && (abs(k[i]) <= g.band[i]);
     }
@@ -136,7 +137,7 @@ __device__ __forceinline__ void green_elastic(const GreenDesc& g, const int* k, 
     bool inband = true, zero = true;
 #pragma unroll
     for (int i = 0; i < DIM; ++i) {
-        xi[i] = (double)k[i] / g.Y[i];
+        xi[i] = (double)k[i] * g.invY[i];
         s += xi[i] * xi[i];
         inband = inband && (abs(k[i]) <= g.band[i]);
         zero = zero && (k[i] == 0);

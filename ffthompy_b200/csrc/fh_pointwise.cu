@@ -907,6 +907,7 @@ static int fill_green(GreenDesc& g, const fh_green* in) {
         g.N[a] = a < in->dim ? (int)in->N[a] : 1;
         g.band[a] = a < in->dim ? (int)in->band[a] : 0;
         g.Y[a] = a < in->dim ? in->Y[a] : 1.0;
+        g.invY[a] = 1.0 / g.Y[a];
     }
     g.c0 = in->c0;
     g.cI = in->cI;

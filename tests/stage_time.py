@@ -39,6 +39,9 @@ out = ['A=%s cfg flags=%d pitch=%d midT=%d env=%s' % (mode, fl.value, pi.value, 
 for st in range(1, 6):
     t = timeit(lambda: L.check(lib.fh_ga_stage(op, st, ptr(x), ptr(y))))
     out.append('S%d %.3f ms %.0f GB/s' % (st, t, alg[st]/t/1e6))
+if lib.fh_ga_stage(op, 6, ptr(x), ptr(y)) == 0:
+    t = timeit(lambda: L.check(lib.fh_ga_stage(op, 6, ptr(x), ptr(y))))
+    out.append('S2-4 chunked %.3f ms' % t)
 t = timeit(lambda: L.check(lib.fh_ga_apply(op, ptr(x), ptr(y))))
 out.append('apply %.3f ms' % t)
 B = torch.randn((D,)+N, dtype=torch.float64, device=dev); xs = torch.zeros_like(B)
