@@ -195,27 +195,14 @@ struct Lut2C {
     double c[2][36];
 };
 
-template <int N, int D, int TRW, int ALAY>
-__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
-    k_fwd_last_fast(const double* __restrict__ A, const unsigned char* __restrict__ phase,
-                    const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
-                    const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
-                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
-    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
-    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
-    constexpr int NT = NP * TPL;
-    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
-    double* smd = reinterpret_cast<double*>(fh_smem_raw);
-    double* zre = smd;              // [NP][NPAD]
-    double* zim = smd + NP * NPAD;  // [NP][NPAD]
-    const int64_t row0 = (int64_t)blockIdx.x * TRW;
-    const int64_t n = nrows * N;  // voxels per component
-    const double beta = pupdate ? scal[3] : 0.0;
-    __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
-    if (ALAY == 2) {
-        for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
-        __syncthreads();
-    }
+// phase 0 of S1: p = r + beta p (optional), sigma = A p on the CTA's TRW x N voxels, two voxels per
+// thread and step (16-byte accesses); store(L, i2, s0, s1) receives sigma of real line L = comp*TRW+row
+// at positions i2, i2+1.
+template <int N, int D, int TRW, int ALAY, int NT, typename Store>
+__device__ __forceinline__ void s1_sigma_phase(const double* __restrict__ A, const unsigned char* __restrict__ phase,
+                                               const double* slut, const Lut2C& lutc, double* __restrict__ p,
+                                               const double* __restrict__ r, double beta, int pupdate, int64_t row0,
+                                               int64_t n, Store store) {
     // phase 0: sigma = A p on TRW x N voxels, two voxels per thread and step (16-byte accesses)
     for (int v = threadIdx.x; v < TRW * (N / 2); v += NT) {
         const int row = v / (N / 2), i2 = 2 * (v - row * (N / 2));
@@ -262,12 +249,38 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
                     s.y += a.y * pv[jj].y;
                 }
             }
-            const int L = i * TRW + row;
-            double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
-            dst[pidx(i2)] = s.x;
-            dst[pidx(i2 + 1)] = s.y;
+            store(i * TRW + row, i2, s.x, s.y);
         }
     }
+}
+
+template <int N, int D, int TRW, int ALAY>
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+    k_fwd_last_fast(const double* __restrict__ A, const unsigned char* __restrict__ phase,
+                    const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
+                    const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
+                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+    constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
+    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
+    constexpr int NT = NP * TPL;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    double* smd = reinterpret_cast<double*>(fh_smem_raw);
+    double* zre = smd;              // [NP][NPAD]
+    double* zim = smd + NP * NPAD;  // [NP][NPAD]
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    const int64_t n = nrows * N;  // voxels per component
+    const double beta = pupdate ? scal[3] : 0.0;
+    __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
+    if (ALAY == 2) {
+        for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
+        __syncthreads();
+    }
+    s1_sigma_phase<N, D, TRW, ALAY, NT>(A, phase, slut, lutc, p, r, beta, pupdate, row0, n,
+                                        [&](int L, int i2, double s0, double s1) {
+                                            double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
+                                            dst[pidx(i2)] = s0;
+                                            dst[pidx(i2 + 1)] = s1;
+                                        });
     __syncthreads();
     const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
     double* lre = zre + pr * NPAD;
@@ -708,5 +721,274 @@ __global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM
 #pragma unroll
             for (int r = 0; r < Ra; ++r) gp[(int64_t)(j + r * Rb) * inner] = v[r];
         }
+    }
+}
+
+// ================================================================== generic in-place power-of-two FFT in
+// shared memory (2 or 3 decimation-in-frequency stages, radices 4/8/16) — brings every power-of-two
+// length that has no register-resident two-pass kernel above (16, 32, 512, 1024, 2048) onto the
+// same pipeline.  L lines are interleaved as buf[pidx(row) * L + line] (complex AoS).
+//   forward (DIF): stage A rows {j + r*N/Ra}, twiddle w_N^(q j); stage B inside blocks of N/Ra with
+//   twiddle w_N^(Ra q j); stage C inside blocks of Rc.  Frequency k = b + Ra*(qb + Rb*s) ends up in
+//   row b*(N/Ra) + qb*Rc + s (digit reversed); smem_row_of_freq() gives the map.  The inverse is the
+//   mirrored network, so both directions are in place.
+template <int N>
+struct Fac3;
+template <>
+struct Fac3<16> {
+    static constexpr int Ra = 4, Rb = 4, Rc = 1;
+};
+template <>
+struct Fac3<32> {
+    static constexpr int Ra = 4, Rb = 8, Rc = 1;
+};
+template <>
+struct Fac3<512> {
+    static constexpr int Ra = 8, Rb = 8, Rc = 8;
+};
+template <>
+struct Fac3<1024> {
+    static constexpr int Ra = 8, Rb = 8, Rc = 16;
+};
+template <>
+struct Fac3<2048> {
+    static constexpr int Ra = 8, Rb = 16, Rc = 16;
+};
+static inline bool fh_gen3_len(int n) { return n == 16 || n == 32 || n == 512 || n == 1024 || n == 2048; }
+
+template <int N>
+__host__ __device__ __forceinline__ int smem_freq_of_row(int row) {
+    constexpr int Ra = Fac3<N>::Ra, Rb = Fac3<N>::Rb, Rc = Fac3<N>::Rc;
+    constexpr int N1 = N / Ra;
+    const int b = row / N1, rem = row - b * N1;
+    const int qb = rem / Rc, s = rem - qb * Rc;
+    return b + Ra * (qb + Rb * s);
+}
+template <int N>
+__host__ __device__ __forceinline__ int smem_row_of_freq(int k) {
+    constexpr int Ra = Fac3<N>::Ra, Rb = Fac3<N>::Rb, Rc = Fac3<N>::Rc;
+    const int b = k % Ra, r1 = k / Ra;
+    const int qb = r1 % Rb, s = r1 / Rb;
+    return b * (N / Ra) + qb * Rc + s;
+}
+
+// one DIF stage over all lines: blocks of NB rows, radix R, twiddle stride TS (w_N^(TS*q*j)); INV
+// runs the mirrored stage (conjugate twiddle before the inverse butterfly)
+template <int N, int NB, int R, int TS, bool INV>
+__device__ __forceinline__ void smem_stage(cplx* __restrict__ buf, int L, const cplx* __restrict__ tw) {
+    constexpr int M = NB / R;               // butterflies per block
+    constexpr int NBF = (N / NB) * M;       // butterflies per line
+    for (int w = threadIdx.x; w < NBF * L; w += blockDim.x) {
+        const int line = w % L, bf = w / L;
+        const int blk = bf / M, j = bf - blk * M;
+        cplx* base = buf + line;
+        const int row0 = blk * NB + j;
+        cplx v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = base[pidx(row0 + r * M) * L];
+        if (INV) {
+            if (M > 1) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, TS * q * j, true));
+            }
+            Bfly<R, true>::run(v);
+        } else {
+            Bfly<R, false>::run(v);
+            if (M > 1) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, TS * q * j, false));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) base[pidx(row0 + r * M) * L] = v[r];
+    }
+}
+
+template <int N, bool INV>
+__device__ __forceinline__ void smem_fft_inplace(cplx* __restrict__ buf, int L, const cplx* __restrict__ tw) {
+    constexpr int Ra = Fac3<N>::Ra, Rb = Fac3<N>::Rb, Rc = Fac3<N>::Rc;
+    if (!INV) {
+        smem_stage<N, N, Ra, 1, false>(buf, L, tw);
+        __syncthreads();
+        smem_stage<N, N / Ra, Rb, Ra, false>(buf, L, tw);
+        __syncthreads();
+        if (Rc > 1) {
+            smem_stage<N, (Rc > 1 ? Rc : 4), (Rc > 1 ? Rc : 4), 1, false>(buf, L, tw);
+            __syncthreads();
+        }
+    } else {
+        if (Rc > 1) {
+            smem_stage<N, (Rc > 1 ? Rc : 4), (Rc > 1 ? Rc : 4), 1, true>(buf, L, tw);
+            __syncthreads();
+        }
+        smem_stage<N, N / Ra, Rb, Ra, true>(buf, L, tw);
+        __syncthreads();
+        smem_stage<N, N, Ra, 1, true>(buf, L, tw);
+        __syncthreads();
+    }
+}
+
+// strided complex axis through the generic routine: [outer][N][inner], T lines per CTA
+template <int N, int T, bool INV>
+__global__ void __launch_bounds__(256) k_c2c_gen3(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                   const cplx* __restrict__ tw, int64_t inner, int ntile, int tile0,
+                                                   double scale) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][T]
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t base = o * N * inner + (int64_t)(tile0 + tile) * T;
+    // natural-order rows in, digit-reversed after the forward DIF (and the other way round for INV)
+    for (int e = threadIdx.x; e < N * T; e += blockDim.x) {
+        const int t = e % T, row = e / T;
+        const int srow = INV ? smem_row_of_freq<N>(row) : row;
+        buf[pidx(srow) * T + t] = in[base + (int64_t)row * inner + t];
+    }
+    __syncthreads();
+    smem_fft_inplace<N, INV>(buf, T, tw);
+    for (int e = threadIdx.x; e < N * T; e += blockDim.x) {
+        const int t = e % T, row = e / T;
+        const int srow = INV ? row : smem_row_of_freq<N>(row);
+        const cplx v = buf[pidx(srow) * T + t];
+        out[base + (int64_t)row * inner + t] = make_double2(v.x * scale, v.y * scale);
+    }
+}
+
+// axis 0 + G^ through the generic routine: data [D][N][inner], tile of T inner positions
+template <int N, int T, int KIND, int DIM>
+__global__ void __launch_bounds__(384) k_mid_green_gen3(cplx* __restrict__ data, const cplx* __restrict__ tw,
+                                                         GreenDesc g, int64_t inner, int nh, int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int L = D * T;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][D*T]
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    for (int e = threadIdx.x; e < D * N * T; e += blockDim.x) {
+        const int t = e % T, row = (e / T) % N, c = e / (T * N);
+        buf[pidx(row) * L + c * T + t] = data[((int64_t)c * N + row) * inner + i0 + t];
+    }
+    __syncthreads();
+    smem_fft_inplace<N, false>(buf, L, tw);
+    for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) {
+        const int row = idx / T, tt = idx - row * T;
+        int k[3];
+        k[0] = fh_freq(smem_freq_of_row<N>(row), N);
+        const int64_t ii = i0 + tt;
+        bool valid = true;
+        if (DIM == 3) {
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
+            k[2] = fh_freq(i2, g.N[2]);
+            valid = i2 < nh;
+        } else {
+            k[1] = fh_freq((int)ii, g.N[1]);
+            k[2] = 0;
+            valid = (int)ii < nh;
+        }
+        cplx* sr = buf + pidx(row) * L + tt;
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * T];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) sr[cc * T] = e[cc];
+    }
+    __syncthreads();
+    smem_fft_inplace<N, true>(buf, L, tw);
+    for (int e = threadIdx.x; e < D * N * T; e += blockDim.x) {
+        const int t = e % T, row = (e / T) % N, c = e / (T * N);
+        data[((int64_t)c * N + row) * inner + i0 + t] = buf[pidx(row) * L + c * T + t];
+    }
+}
+
+// ------------------------------------------------------------------ last axis through the generic routine
+// S1: sigma = A p (+ p update), two real lines per complex line, in-place DIF, separation -> spectrum.
+// The NP = D*TRW/2 complex lines sit in buf[pidx(row) * NP + pair] (re = even real line, im = odd).
+template <int N, int D, int TRW, int ALAY>
+__global__ void __launch_bounds__(256)
+    k_fwd_last_gen3(const double* __restrict__ A, const unsigned char* __restrict__ phase,
+                    const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
+                    const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
+                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+    constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][NP]
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    const int64_t n = nrows * N;
+    const double beta = pupdate ? scal[3] : 0.0;
+    __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
+    if (ALAY == 2) {
+        for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
+        __syncthreads();
+    }
+    double* bd = reinterpret_cast<double*>(buf);
+    s1_sigma_phase<N, D, TRW, ALAY, NT>(A, phase, slut, lutc, p, r, beta, pupdate, row0, n,
+                                        [&](int L, int i2, double s0, double s1) {
+                                            const int pr = L >> 1, part = L & 1;
+                                            bd[2 * (pidx(i2) * NP + pr) + part] = s0;
+                                            bd[2 * (pidx(i2 + 1) * NP + pr) + part] = s1;
+                                        });
+    __syncthreads();
+    smem_fft_inplace<N, false>(buf, NP, tw);
+    for (int it = threadIdx.x; it < NL * pitch; it += NT) {
+        const int L = it / pitch, k = it - L * pitch;
+        const int c = L / TRW, row = L - c * TRW;
+        cplx X = make_double2(0.0, 0.0);
+        if (k < nh) {
+            const int km = (k == 0) ? 0 : N - k;
+            const cplx a = buf[pidx(smem_row_of_freq<N>(k)) * NP + (L >> 1)];
+            const cplx b = buf[pidx(smem_row_of_freq<N>(km)) * NP + (L >> 1)];
+            X = (L & 1) ? make_double2(0.5 * (a.y + b.y), -0.5 * (a.x - b.x))
+                        : make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+        }
+        spec[((size_t)c * nrows + row0 + row) * pitch + k] = X;
+    }
+}
+
+// S5: Hermitian completion of two half spectra into one complex line, mirrored inverse in place,
+// re/im -> the two real lines (x scale), optional partial sums of <pdot, y>.
+template <int N, int D, int TRW>
+__global__ void __launch_bounds__(256)
+    k_inv_last_gen3(const cplx* __restrict__ spec, double* __restrict__ y, const double* __restrict__ pdot,
+                    double* __restrict__ part, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
+                    double scale) {
+    constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    __shared__ double red[32];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    for (int it = threadIdx.x; it < NP * nh; it += NT) {
+        const int pr = it / nh, k = it - pr * nh;
+        const int La = 2 * pr, Lb = 2 * pr + 1;
+        const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
+        cplx a = spec[((size_t)ca * nrows + row0 + ra) * pitch + k];
+        cplx b = spec[((size_t)cb * nrows + row0 + rb) * pitch + k];
+        if (k == 0 || 2 * k == N) {
+            a.y = 0.0;
+            b.y = 0.0;
+        }
+        buf[pidx(smem_row_of_freq<N>(k)) * NP + pr] = make_double2(a.x - b.y, a.y + b.x);
+        if (k > 0 && 2 * k != N) buf[pidx(smem_row_of_freq<N>(N - k)) * NP + pr] = make_double2(a.x + b.y, -a.y + b.x);
+    }
+    __syncthreads();
+    smem_fft_inplace<N, true>(buf, NP, tw);
+    double acc = 0.0;
+    for (int it = threadIdx.x; it < NL * N; it += NT) {
+        const int L = it / N, i2 = it - L * N;
+        const int c = L / TRW, row = L - c * TRW;
+        const cplx z = buf[pidx(i2) * NP + (L >> 1)];
+        const double v = ((L & 1) ? z.y : z.x) * scale;
+        const size_t o = ((size_t)c * nrows + row0 + row) * N + i2;
+        y[o] = v;
+        if (pdot) acc += pdot[o] * v;
+    }
+    if (pdot) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) part[blockIdx.x] = acc;
     }
 }

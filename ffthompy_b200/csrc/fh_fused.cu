@@ -24,7 +24,7 @@
 int fh_fill_green(GreenDesc& g, const fh_green* in);
 
 #define GA_NT 256
-#define GA_MAXPART 65536
+#define GA_MAXPART 524288
 
 struct fh_ga {
     const fh_plan* plan;
@@ -204,9 +204,31 @@ static int launch_c2c_fast_NT(const cplx* tw, cplx* data, int64_t outer, int64_t
     return FH_OK;
 }
 
+template <int N, int T>
+static int launch_c2c_gen3_NT(const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv) {
+    const size_t smem = (size_t)(N + N / 16) * T * sizeof(cplx);
+    const int ntile = (int)(inner / T);
+    const unsigned nblk = (unsigned)(outer * ntile);
+    int rc;
+    if (inv) {
+        if ((rc = smem_attr(k_c2c_gen3<N, T, true>, smem))) return rc;
+        k_c2c_gen3<N, T, true><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, inner, ntile, 0, 1.0);
+    } else {
+        if ((rc = smem_attr(k_c2c_gen3<N, T, false>, smem))) return rc;
+        k_c2c_gen3<N, T, false><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, inner, ntile, 0, 1.0);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
 static int launch_c2c_fast(int N, const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, int col0 = 0,
                            int ncols = 0) {
     switch (N) {
+        case 16: return launch_c2c_gen3_NT<16, 8>(tw, data, outer, inner, inv);
+        case 32: return launch_c2c_gen3_NT<32, 8>(tw, data, outer, inner, inv);
+        case 512: return launch_c2c_gen3_NT<512, 8>(tw, data, outer, inner, inv);
+        case 1024: return launch_c2c_gen3_NT<1024, 8>(tw, data, outer, inner, inv);
+        case 2048: return launch_c2c_gen3_NT<2048, 4>(tw, data, outer, inner, inv);
         case 64: return launch_c2c_fast_NT<64, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
         case 128: return launch_c2c_fast_NT<128, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
         case 256: return launch_c2c_fast_NT<256, 8>(tw, data, outer, inner, inv, 1.0, col0, ncols);
@@ -262,10 +284,31 @@ static int launch_mid_2r_NT(fh_ga* op) {
     return FH_OK;
 }
 
+template <int N, int T, int KIND, int DIM>
+static int launch_mid_gen3_NT(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const fh_plan* p = op->plan;
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
+    const size_t smem = (size_t)(N + N / 16) * D * T * sizeof(cplx);
+    if (smem > (size_t)fh_max_smem_optin())
+        return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: N0=%d D=%d does not fit shared memory", N, D);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_gen3<N, T, KIND, DIM>, smem))) return rc;
+    k_mid_green_gen3<N, T, KIND, DIM><<<(unsigned)(inner / T), 384, smem, fh_stream()>>>(op->specT, p->ax[0].tw, op->g,
+                                                                                      inner, p->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
 template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
+    if (N == 16) return launch_mid_gen3_NT<16, 4, KIND, DIM>(op);
+    if (N == 32) return launch_mid_gen3_NT<32, 4, KIND, DIM>(op);
+    if (N == 512) return launch_mid_gen3_NT<512, 2, KIND, DIM>(op);
+    if (N == 1024) return launch_mid_gen3_NT<1024, 2, KIND, DIM>(op);
+    if (N == 2048) return launch_mid_gen3_NT<2048, 1, KIND, DIM>(op);
     if (op->mid_pipe == 9 && N == 256) {  // debugging: data movement only
         constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
         const fh_plan* p = op->plan;
@@ -349,6 +392,78 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     return FH_OK;
 }
 
+template <int N, int D, int TRW, int ALAY>
+static int launch_fwd_last_g3A(fh_ga* op, double* p, const double* r, int pupdate) {
+    constexpr int NP = D * TRW / 2;
+    const size_t smem = (size_t)(N + N / 16) * NP * sizeof(cplx);
+    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const fh_plan* pl = op->plan;
+    int rc;
+    if ((rc = smem_attr(k_fwd_last_gen3<N, D, TRW, ALAY>, smem))) return rc;
+    k_fwd_last_gen3<N, D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p,
+                                                                       r, op->scal, pupdate, op->spec,
+                                                                       pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
+                                                                       op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+template <int N, int D, int TRW>
+static int launch_fwd_last_g3(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    if (!withA) return launch_fwd_last_g3A<N, D, TRW, -1>(op, p, r, pupdate);
+    if (op->a_mode == 2 && op->nphase <= 2 && D * D <= 36) return launch_fwd_last_g3A<N, D, TRW, 3>(op, p, r, pupdate);
+    if (op->a_mode == 2) return launch_fwd_last_g3A<N, D, TRW, 2>(op, p, r, pupdate);
+    if (op->a_mode == 1) return launch_fwd_last_g3A<N, D, TRW, 1>(op, p, r, pupdate);
+    return launch_fwd_last_g3A<N, D, TRW, 0>(op, p, r, pupdate);
+}
+template <int N, int D, int TRW>
+static int launch_inv_last_g3(fh_ga* op, double* y, const double* pdot, int* npart) {
+    constexpr int NP = D * TRW / 2;
+    const size_t smem = (size_t)(N + N / 16) * NP * sizeof(cplx);
+    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const fh_plan* pl = op->plan;
+    int rc;
+    if ((rc = smem_attr(k_inv_last_gen3<N, D, TRW>, smem))) return rc;
+    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_gen3<N, D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[pl->dim - 1].tw,
+                                                                 op->nrows, pl->nh, op->pitch, 1.0 / (double)pl->nreal);
+    FH_LAUNCH_CHECK();
+    if (npart) *npart = (int)nblk;
+    return FH_OK;
+}
+
+// generic-routine sizes: TRW = 2 rows per CTA (D even) or 4 (D = 3)
+#define FH_LAST_DISPATCH_G3(FN, ...)                                             \
+    do {                                                                         \
+        const int N_ = op->plan->N[op->plan->dim - 1];                           \
+        const int D_ = op->D;                                                    \
+        if (D_ == 6) {                                                           \
+            if (N_ == 16) return FN<16, 6, 2>(__VA_ARGS__);                      \
+            if (N_ == 32) return FN<32, 6, 2>(__VA_ARGS__);                      \
+            if (N_ == 512) return FN<512, 6, 2>(__VA_ARGS__);                    \
+            if (N_ == 1024) return FN<1024, 6, 2>(__VA_ARGS__);                  \
+            if (N_ == 2048) return FN<2048, 6, 2>(__VA_ARGS__);                  \
+        } else if (D_ == 3) {                                                    \
+            if (N_ == 16) return FN<16, 3, 4>(__VA_ARGS__);                      \
+            if (N_ == 32) return FN<32, 3, 4>(__VA_ARGS__);                      \
+            if (N_ == 512) return FN<512, 3, 4>(__VA_ARGS__);                    \
+            if (N_ == 1024) return FN<1024, 3, 4>(__VA_ARGS__);                  \
+            if (N_ == 2048) return FN<2048, 3, 4>(__VA_ARGS__);                  \
+        } else if (D_ == 2) {                                                    \
+            if (N_ == 16) return FN<16, 2, 4>(__VA_ARGS__);                      \
+            if (N_ == 32) return FN<32, 2, 4>(__VA_ARGS__);                      \
+            if (N_ == 512) return FN<512, 2, 4>(__VA_ARGS__);                    \
+            if (N_ == 1024) return FN<1024, 2, 4>(__VA_ARGS__);                  \
+            if (N_ == 2048) return FN<2048, 2, 4>(__VA_ARGS__);                  \
+        }                                                                        \
+        return fh_set_error(FH_ERR_UNSUPPORTED, "no generic-routine last-axis kernel"); \
+    } while (0)
+static int launch_fwd_last_gen3(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    FH_LAST_DISPATCH_G3(launch_fwd_last_g3, op, p, r, pupdate, withA);
+}
+static int launch_inv_last_gen3(fh_ga* op, double* y, const double* pdot, int* npart) {
+    FH_LAST_DISPATCH_G3(launch_inv_last_g3, op, y, pdot, npart);
+}
+
 #define FH_LAST_DISPATCH(FN, ...)                                            \
     do {                                                                     \
         const int N_ = op->plan->N[op->plan->dim - 1];                       \
@@ -374,12 +489,17 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     } while (0)
 
 static int launch_fwd_last_fast(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_fwd_last_gen3(op, p, r, pupdate, withA);
     FH_LAST_DISPATCH(launch_fwd_last_NT, op, p, r, pupdate, withA);
 }
 static int launch_inv_last_fast(fh_ga* op, double* y, const double* pdot, int* npart) {
+    if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_inv_last_gen3(op, y, pdot, npart);
     FH_LAST_DISPATCH(launch_inv_last_NT, op, y, pdot, npart);
 }
-static int trw_for(int D) { return D == 6 ? 4 : 8; }
+static int trw_for(int D, int nlast) {
+    if (fh_gen3_len(nlast)) return D == 6 ? 2 : 4;
+    return D == 6 ? 4 : 8;
+}
 
 // ------------------------------------------------------------------ coefficient analysis (once per operator)
 // exact symmetry check: flag != 0 if any A_ij != A_ji
@@ -539,17 +659,19 @@ static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, i
     op->spec = (cplx*)(work + round16((int64_t)D * op->nloc));
     op->specT = slab ? op->spec + (size_t)D * op->nspecp : op->spec;
     const int use_fast = env_int("FH_FAST", 1);
-    op->trw = trw_for(D);
-    if (D == 6 && env_int("FH_TRW", 4) == 2) op->trw = 2;
-    op->fast_last = use_fast && fh_fast_len(plan->N[d - 1]) && (op->nrows % op->trw == 0);
-    op->fast_mid1 = use_fast && d == 3 && fh_fast_len(plan->N[1]);
-    op->fast_mid0 = use_fast && fh_fast_len(plan->N[0]) && (((int64_t)op->n1l * op->pitch) % 4 == 0);
+    op->trw = trw_for(D, plan->N[d - 1]);
+    if (D == 6 && !fh_gen3_len(plan->N[d - 1]) && env_int("FH_TRW", 4) == 2) op->trw = 2;
+    auto pow2fast = [](int n) { return fh_fast_len(n) || fh_gen3_len(n); };
+    op->fast_last = use_fast && pow2fast(plan->N[d - 1]) && (op->nrows % op->trw == 0);
+    op->fast_mid1 = use_fast && d == 3 && pow2fast(plan->N[1]);
+    op->fast_mid0 = use_fast && pow2fast(plan->N[0]) && (((int64_t)op->n1l * op->pitch) % 4 == 0);
     op->mid_T = env_int("FH_MID_T", 4);
     op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
     // L2 blocking (3-D, all-fast, not slab-decomposed): chunk = FH_CHUNK columns (default 8 = one S2 tile)
     op->chunk_cols = 0;
-    if (d == 3 && !slab && op->fast_mid0 && op->fast_mid1 && op->mid_T == 4 && op->mid_pipe != 0 && op->mid_pipe != 9) {
+    if (d == 3 && !slab && op->fast_mid0 && op->fast_mid1 && fh_fast_len(plan->N[0]) && fh_fast_len(plan->N[1]) &&
+        op->mid_T == 4 && op->mid_pipe != 0 && op->mid_pipe != 9) {
         int cc = env_int("FH_CHUNK", 0);  // off by default: measured slower than whole-row launches
         if (cc > 0 && cc % 8 == 0 && cc < op->pitch) op->chunk_cols = cc;
     }
