@@ -81,12 +81,39 @@ static void factorize(int n, AxisDesc& ax) {
         int base = e2 / np, extra = e2 % np;
         for (int i = 0; i < np; ++i) ax.fac[ax.nfac++] = 1 << (base + (i < extra ? 1 : 0));
     }
+    // odd part: prime factors, with pairs of small ones merged into the composite radices 9 and 15
+    // (one register pass instead of two)
+    int odd[FH_MAX_FAC + 8], nodd = 0;
     for (int p = 3; (int64_t)p * p <= m; p += 2)
-        while (m % p == 0) {
-            ax.fac[ax.nfac++] = p;
+        while (m % p == 0 && nodd < FH_MAX_FAC + 8) {
+            odd[nodd++] = p;
             m /= p;
         }
-    if (m > 1) ax.fac[ax.nfac++] = m;
+    if (m > 1) odd[nodd++] = m;
+    bool used[FH_MAX_FAC + 8] = {false};
+    for (int i = 0; i < nodd; ++i) {
+        if (used[i]) continue;
+        int r = odd[i];
+        if (r == 3) {
+            for (int j = i + 1; j < nodd; ++j)
+                if (!used[j] && (odd[j] == 5 || odd[j] == 3)) {
+                    // prefer 3*5 = 15, else 3*3 = 9
+                    int pick = -1;
+                    for (int k = i + 1; k < nodd; ++k)
+                        if (!used[k] && odd[k] == 5) {
+                            pick = k;
+                            break;
+                        }
+                    if (pick < 0) pick = j;
+                    r *= odd[pick];
+                    used[pick] = true;
+                    break;
+                }
+        }
+        used[i] = true;
+        if (ax.nfac < FH_MAX_FAC) ax.fac[ax.nfac] = r;
+        ax.nfac++;
+    }
 }
 
 extern "C" int fh_plan_create(fh_plan** out, int dim, const int64_t* N) {
@@ -166,11 +193,26 @@ __global__ void __launch_bounds__(256) k_c2c_strided(const cplx* __restrict__ in
     const int64_t i0 = (int64_t)tile * T;
     const int nl = (int)min((int64_t)T, inner - i0);
     const int64_t base = o * n * inner + i0;
-    for (int idx = threadIdx.x; idx < n * nl; idx += blockDim.x) {
-        const int row = idx / nl, t = idx - row * nl;
-        const cplx c = in[base + (int64_t)row * inner + t];
-        b0re[row * ld + t] = c.x;
-        b0im[row * ld + t] = c.y;
+    // 4 independent 16-byte loads in flight per thread
+    for (int idx0 = threadIdx.x; idx0 < n * nl; idx0 += 4 * blockDim.x) {
+        cplx c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            if (idx < n * nl) {
+                const int row = idx / nl, t = idx - row * nl;
+                c[u] = in[base + (int64_t)row * inner + t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            if (idx < n * nl) {
+                const int row = idx / nl, t = idx - row * nl;
+                b0re[row * ld + t] = c[u].x;
+                b0im[row * ld + t] = c[u].y;
+            }
+        }
     }
     __syncthreads();
     const int cur = fft_smem<INV>(b0re, b0im, b1re, b1im, ax, nl, ld);
@@ -196,13 +238,28 @@ __global__ void __launch_bounds__(256) k_r2c_last(const double* __restrict__ x, 
     const int64_t line0 = (int64_t)blockIdx.x * 2 * LP;
     const int nll = (int)min((int64_t)2 * LP, nlines - line0);
     const int npairs = (nll + 1) >> 1;
-    for (int idx = threadIdx.x; idx < 2 * npairs * n; idx += blockDim.x) {
-        const int l = idx / n, i = idx - l * n;
-        const double v = (l < nll) ? x[(line0 + l) * n + i] : 0.0;
-        if (l & 1)
-            b0im[i * ld + (l >> 1)] = v;
-        else
-            b0re[i * ld + (l >> 1)] = v;
+    for (int idx0 = threadIdx.x; idx0 < 2 * npairs * n; idx0 += 4 * blockDim.x) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            v[u] = 0.0;
+            if (idx < 2 * npairs * n) {
+                const int l = idx / n, i = idx - l * n;
+                if (l < nll) v[u] = x[(line0 + l) * n + i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            if (idx < 2 * npairs * n) {
+                const int l = idx / n, i = idx - l * n;
+                if (l & 1)
+                    b0im[i * ld + (l >> 1)] = v[u];
+                else
+                    b0re[i * ld + (l >> 1)] = v[u];
+            }
+        }
     }
     __syncthreads();
     const int cur = fft_smem<false>(b0re, b0im, b1re, b1im, ax, npairs, ld);
@@ -237,7 +294,10 @@ __global__ void __launch_bounds__(256) k_c2r_last(const cplx* __restrict__ X, do
     const int64_t line0 = (int64_t)blockIdx.x * 2 * LP;
     const int nll = (int)min((int64_t)2 * LP, nlines - line0);
     const int npairs = (nll + 1) >> 1;
-    for (int idx = threadIdx.x; idx < npairs * nh; idx += blockDim.x) {
+    for (int idx0 = threadIdx.x; idx0 < npairs * nh; idx0 += 2 * blockDim.x)
+      for (int u = 0; u < 2; ++u) {
+        const int idx = idx0 + u * blockDim.x;
+        if (idx >= npairs * nh) break;
         const int pr = idx / nh, k = idx - pr * nh;
         const int64_t la = line0 + 2 * pr;
         cplx a = X[la * pitch + k];

@@ -14,6 +14,7 @@
 // is in natural order and no bit-reversal pass exists.
 #pragma once
 #include "fh_common.cuh"
+#include "fh_roots.cuh"
 
 #define FH_MAX_FAC 12
 
@@ -117,27 +118,47 @@ struct Bfly<16, INV> {
     }
 };
 
-// Direct O(R^2) DFT for small odd radices; roots taken from the axis twiddle
-// table: exp(-2*pi*i*m/R) = tw[m * (n/R)].
+// Odd-radix butterflies (3, 5, 7, 9, 11, 13, 15, 17, 19): direct DFT in its conjugate-symmetric form,
+//   a_r = v_r + v_{R-r},  b_r = v_r - v_{R-r}   (r = 1..h, h = (R-1)/2)
+//   y_q, y_{R-q} = v_0 + sum_r a_r cos(2 pi q r/R)  -/+  i * sum_r b_r sin(2 pi q r/R)   (forward)
+// i.e. (R-1)^2 real FMAs per butterfly; the roots are compile-time constants (fh_roots.cuh).
 template <int R, bool INV>
-__device__ __forceinline__ void bfly_direct(cplx* v, const cplx* __restrict__ tw, int nR) {
-    cplx root[R];
+__device__ __forceinline__ void bfly_direct(cplx* v, const cplx* __restrict__ /*tw*/, int /*nR*/) {
+    constexpr int H = (R - 1) / 2;
+    cplx a[H], b[H];
 #pragma unroll
-    for (int m = 0; m < R; ++m) {
-        cplx w = __ldg(&tw[m * nR]);
-        root[m] = INV ? cconj(w) : w;
+    for (int r = 1; r <= H; ++r) {
+        a[r - 1] = cadd(v[r], v[R - r]);
+        b[r - 1] = csub(v[r], v[R - r]);
+    }
+    cplx y0 = v[0];
+#pragma unroll
+    for (int r = 0; r < H; ++r) {
+        y0.x += a[r].x;
+        y0.y += a[r].y;
     }
     cplx y[R];
+    y[0] = y0;
 #pragma unroll
-    for (int q = 0; q < R; ++q) {
-        cplx acc = v[0];
+    for (int q = 1; q <= H; ++q) {
+        double sx = v[0].x, sy = v[0].y, tx = 0.0, ty = 0.0;
 #pragma unroll
-        for (int r = 1; r < R; ++r) {
-            const cplx w = root[(q * r) % R];
-            acc.x += v[r].x * w.x - v[r].y * w.y;
-            acc.y += v[r].x * w.y + v[r].y * w.x;
+        for (int r = 1; r <= H; ++r) {
+            const double c = OddRoots<R>::c((q * r) % R);
+            const double sn = OddRoots<R>::s((q * r) % R);
+            sx += a[r - 1].x * c;
+            sy += a[r - 1].y * c;
+            tx += b[r - 1].y * sn;
+            ty += b[r - 1].x * sn;
         }
-        y[q] = acc;
+        // forward: v e^{-i t}: real a.x c + b.y s, imag a.y c - b.x s ; inverse: signs of s flipped
+        if (INV) {
+            y[q] = make_double2(sx - tx, sy + ty);
+            y[R - q] = make_double2(sx + tx, sy - ty);
+        } else {
+            y[q] = make_double2(sx + tx, sy - ty);
+            y[R - q] = make_double2(sx - tx, sy + ty);
+        }
     }
 #pragma unroll
     for (int q = 0; q < R; ++q) v[q] = y[q];
@@ -246,6 +267,12 @@ __device__ __forceinline__ int fft_smem(double* b0re, double* b0im, double* b1re
             case 7: stockham_pass<7, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
             case 8: stockham_pass<8, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
             case 16: stockham_pass<16, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 9: stockham_pass<9, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 11: stockham_pass<11, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 13: stockham_pass<13, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 15: stockham_pass<15, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 17: stockham_pass<17, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
+            case 19: stockham_pass<19, INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, ax.tw); break;
             default: stockham_pass_prime<INV>(ire, iim, ore, oim, ax.n, nl, ld, Ns, R, ax.tw); break;
         }
         __syncthreads();

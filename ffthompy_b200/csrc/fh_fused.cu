@@ -99,12 +99,27 @@ __global__ void __launch_bounds__(GA_NT) k_mid_green(cplx* __restrict__ data, Ax
     const int64_t i0 = (int64_t)blockIdx.x * T;
     const int nl = (int)min((int64_t)T, inner - i0);
     const int nln = n * nl;
-    for (int idx = threadIdx.x; idx < D * nln; idx += blockDim.x) {
-        const int c = idx / nln, rem = idx - c * nln;
-        const int row = rem / nl, t = rem - row * nl;
-        const cplx v = data[((int64_t)c * n + row) * inner + i0 + t];
-        b0re[row * ld + c * nl + t] = v.x;
-        b0im[row * ld + c * nl + t] = v.y;
+    for (int idx0 = threadIdx.x; idx0 < D * nln; idx0 += 4 * blockDim.x) {
+        cplx v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            if (idx < D * nln) {
+                const int c = idx / nln, rem = idx - c * nln;
+                const int row = rem / nl, t = rem - row * nl;
+                v[u] = data[((int64_t)c * n + row) * inner + i0 + t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int idx = idx0 + u * blockDim.x;
+            if (idx < D * nln) {
+                const int c = idx / nln, rem = idx - c * nln;
+                const int row = rem / nl, t = rem - row * nl;
+                b0re[row * ld + c * nl + t] = v[u].x;
+                b0im[row * ld + c * nl + t] = v[u].y;
+            }
+        }
     }
     __syncthreads();
     int cur = fft_smem<false>(b0re, b0im, b1re, b1im, ax, D * nl, ld);
