@@ -262,10 +262,21 @@ def run_ours(args):
         torch.cuda.synchronize()
         stage_ms[st] = e0.elapsed_time(e1)/K
     dom = max(stage_ms, key=lambda s: stage_ms[s])
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (profiles/), if it is the same kernel
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fjs:
+            tj = json.load(fjs)['dram_bytes_per_launch']
+        tag = {1: 'k_fwd_last_fast', 2: 'k_c2c_fast<256, 8, 0>', 3: 'k_mid_green_pipe', 4: 'k_c2c_fast<256, 8, 1>',
+               5: 'k_inv_last_fast'}[dom]
+        if n == 256:
+            traffic = [v for k, v in tj.items() if k.startswith(tag)][0]
+    except Exception:
+        traffic = None
     achieved = alg[dom]/(stage_ms[dom]*1e-3)/1e9
     B_iter = 15*F+8.*21*nvox  # 15F + C_A (symmetric-packed A) = 888 n bytes
     roofline = {'bound': 'hbm', 'kernel': names[dom], 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                'frac': achieved/peak, 'traffic': None, 'peak_source': peak_src,
+                'frac': achieved/peak, 'traffic': traffic, 'peak_source': peak_src,
                 'algorithmic_bytes_per_launch': alg[dom],
                 'stages': {names[s]: {'ms': stage_ms[s], 'GB/s': alg[s]/(stage_ms[s]*1e-3)/1e9,
                                       'share_of_step': stage_ms[s]/ms_step} for s in stage_ms},
