@@ -75,6 +75,7 @@ _SIGNATURES = {
     'fh_ga_create_slab': (c_int, [C.POINTER(c_vp), c_vp, c_int, c_vp, c_int, C.POINTER(fh_green), c_vp, c_int, c_int,
                                   c_int]),
     'fh_ga_buffers': (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), p_int]),
+    'fh_ga_last_dot': (c_int, [c_vp, p_dbl]),
     'fh_cg_xr_update': (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, p_dbl]),
     'fh_cg_p_update': (c_int, [c_i64, c_vp, c_vp, c_dbl]),
     'fh_ga_destroy': (c_int, [c_vp]),

@@ -58,6 +58,7 @@ struct fh_ga {
     // CG state (fh_cg_begin / fh_cg_steps)
     int64_t kit;
     int have_beta;
+    int last_npart;  // partial sums left in `part` by the last stage-5 launch
 };
 
 static int env_int(const char* name, int dflt) {
@@ -984,7 +985,28 @@ extern "C" int fh_ga_stage(fh_ga* op, int stage, const double* x, double* y) {
     FH_REQUIRE(op && x && y, "fh_ga_stage: null argument");
     if (stage == 6) return op->chunk_cols > 0 ? ga_mid_chunked(op) : fh_set_error(FH_ERR_ARG, "stage 6: L2 blocking is off");
     int np = 0;
-    return ga_stage(op, stage, (double*)x, NULL, 0, y, 1, &np);
+    const int rc = ga_stage(op, stage, (double*)x, NULL, 0, y, 1, &np);
+    if (stage == 5 && !rc) op->last_npart = np;
+    return rc;
+}
+
+// sum of the partial <x,y> left by the last stage-5 launch (this rank's part, not normalised)
+__global__ void k_sum_part(int np, const double* __restrict__ part, double* __restrict__ out) {
+    __shared__ double red[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc += part[i];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+extern "C" int fh_ga_last_dot(fh_ga* op, double* result_host) {
+    FH_REQUIRE(op && result_host, "fh_ga_last_dot: null argument");
+    FH_REQUIRE(op->last_npart > 0, "fh_ga_last_dot: no stage-5 partial sums available");
+    k_sum_part<<<1, GA_NT, 0, fh_stream()>>>(op->last_npart, op->part, op->scal + 8);
+    FH_LAUNCH_CHECK();
+    FH_CUDA(cudaMemcpyAsync(op->pinned, op->scal + 8, sizeof(double), cudaMemcpyDeviceToHost, fh_stream()));
+    FH_CUDA(cudaStreamSynchronize(fh_stream()));
+    *result_host = op->pinned[0];
+    return FH_OK;
 }
 
 static int read_norm(fh_ga* op, double* out) {

@@ -34,9 +34,10 @@ class SlabLayout(object):
         self.nh = self.N[2]//2+1
 
 
-def exchange_fwd(spec, layout, group=None):
+def exchange_fwd(spec, layout, group=None, out=None):
     """x-slabs -> y-slabs: spec [D][n0l][N1][P] (this rank's planes, all k1) ->
-    [D][N0][n1l][P] (all k0, this rank's k1 range).  One all_to_all_single."""
+    [D][N0][n1l][P] (all k0, this rank's k1 range).  One pack, one all_to_all_single, one unpack
+    (written straight into `out` when given)."""
     import torch
     import torch.distributed as dist
     D, n0l, N1, P = spec.shape
@@ -44,10 +45,13 @@ def exchange_fwd(spec, layout, group=None):
     send = spec.reshape(D, n0l, G, n1l, P).permute(2, 0, 1, 3, 4).contiguous()   # [G][D][n0l][n1l][P]
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
-    return recv.permute(1, 0, 2, 3, 4).reshape(D, G*n0l, n1l, P)                  # [D][N0][n1l][P]
+    if out is None:
+        return recv.permute(1, 0, 2, 3, 4).reshape(D, G*n0l, n1l, P)              # [D][N0][n1l][P]
+    out.view(D, G, n0l, n1l, P).copy_(recv.permute(1, 0, 2, 3, 4))
+    return out
 
 
-def exchange_bwd(specT, layout, group=None):
+def exchange_bwd(specT, layout, group=None, out=None):
     """y-slabs -> x-slabs (inverse of exchange_fwd)."""
     import torch
     import torch.distributed as dist
@@ -56,7 +60,10 @@ def exchange_bwd(specT, layout, group=None):
     send = specT.reshape(D, G, n0l, n1l, P).permute(1, 0, 2, 3, 4).contiguous()   # [G][D][n0l][n1l][P]
     recv = torch.empty_like(send)
     dist.all_to_all_single(recv, send, group=group)
-    return recv.permute(1, 2, 0, 3, 4).reshape(D, n0l, G*n1l, P)                  # [D][n0l][N1][P]
+    if out is None:
+        return recv.permute(1, 2, 0, 3, 4).reshape(D, n0l, G*n1l, P)              # [D][n0l][N1][P]
+    out.view(D, n0l, G, n1l, P).copy_(recv.permute(1, 2, 0, 3, 4))
+    return out
 
 
 def allreduce_sum(value, device, group=None):
@@ -122,15 +129,22 @@ class SlabGA(object):
         self._stage(1, x, y)
         self._stage(2, x, y)
         if self.layout.world > 1:
-            self.specT.copy_(exchange_fwd(self.spec, self.layout, self.group))
+            exchange_fwd(self.spec, self.layout, self.group, out=self.specT)
             self.exchanged_bytes += self.spec.numel()*16*(self.layout.world-1)//self.layout.world
         self._stage(3, x, y)
         if self.layout.world > 1:
-            self.spec.copy_(exchange_bwd(self.specT, self.layout, self.group))
+            exchange_bwd(self.specT, self.layout, self.group, out=self.spec)
             self.exchanged_bytes += self.spec.numel()*16*(self.layout.world-1)//self.layout.world
         self._stage(4, x, y)
         self._stage(5, x, y)
         return y
+
+    def last_dot(self):
+        """global <x, y> of the most recent apply(x, y): S5 already left this rank's partial sums on the
+        device (no extra pass over the fields)"""
+        loc = C.c_double()
+        self.L.check(self.dev.lib().fh_ga_last_dot(self.handle, C.byref(loc)))
+        return allreduce_sum(loc.value, self.dev.device(), self.group)/self.pN
 
     def dot(self, a, b):
         """global <a,b> = sum over all ranks / prod(N)  (Tensor scalar product, tensors/objects.py:635)"""
@@ -153,7 +167,7 @@ class SlabGA(object):
         while norm_res > tol and kit < maxiter:
             kit += 1
             self.apply(p, Ap)
-            alp = rr/self.dot(p, Ap)
+            alp = rr/self.last_dot()
             loc = C.c_double()
             L.check(lib.fh_cg_xr_update(n, dev.ptr(x), dev.ptr(r), dev.ptr(p), dev.ptr(Ap), float(alp), C.byref(loc)))
             rrnext = allreduce_sum(loc.value, x.device, self.group)/self.pN

@@ -132,6 +132,8 @@ int64_t fh_ga_slab_work_doubles(const fh_plan* plan, int D, int n0_local, int n1
 int fh_ga_create_slab(fh_ga** op, const fh_plan* plan, int D, const double* A_local, int a_layout, const fh_green* g,
                       double* work, int n0_local, int n1_local, int n1_offset);
 int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch);
+/* this rank's sum of x*y left on the device by the last fh_ga_stage(op, 5, x, y) */
+int fh_ga_last_dot(fh_ga* op, double* result_host);
 int fh_ga_destroy(fh_ga* op);
 int fh_ga_apply(fh_ga* op, const double* x, double* y);
 /* flags: bit0/1/2 = register-resident power-of-two kernels on the last axis / axis 1 / axis 0 */
