@@ -8,8 +8,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
 SOURCES = ['fh_fft.cu', 'fh_pointwise.cu', 'fh_fused.cu']
-HEADERS = ['fh_common.cuh', 'fh_fft.cuh', 'fh_green.cuh', 'fh_plan.cuh',
-           os.path.join('..', '..', 'include', 'ffthom_b200.h')]
+HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith('.cuh')) + [os.path.join('..', '..', 'include', 'ffthom_b200.h')]
 LIB = os.path.join(PKG, 'libffthom_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

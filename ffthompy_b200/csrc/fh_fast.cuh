@@ -992,3 +992,344 @@ __global__ void __launch_bounds__(256)
         if (threadIdx.x == 0) part[blockIdx.x] = acc;
     }
 }
+
+// ================================================================== run-time-length version of the in-place
+// routine: N = R0*R1*R2 with up to three radices from {2,3,4,5,7,8,9,11,13,15,16,17,19}.  This puts the
+// odd "doubled" grids of the exact-integration scheme (Nbar = 2N-1: 255 = 15*17, 243 = 9*9*3, 225 = 15*15,
+// 125 = 5*5*5, 63 = 9*7, ...) on the same fused five-stage pipeline as the powers of two.
+struct RtPlan {
+    int n;      // length
+    int ns;     // number of stages (1..3)
+    int R[3];   // radices, DIF order
+    int NB[3];  // block size of stage s:  n, n/R0, n/(R0*R1)
+    int TS[3];  // twiddle stride of stage s: 1, R0, R0*R1
+    int npr;    // padded rows: n + n/16 + 1
+};
+
+__device__ __forceinline__ int rt_freq_of_row(const RtPlan& P, int row) {
+    int k = 0, mul = 1, rem = row;
+    for (int s = 0; s < P.ns; ++s) {
+        const int sub = P.NB[s] / P.R[s];  // rows per digit step at this stage
+        const int dgt = rem / sub;
+        rem -= dgt * sub;
+        k += dgt * mul;
+        mul *= P.R[s];
+    }
+    return k;
+}
+__device__ __forceinline__ int rt_row_of_freq(const RtPlan& P, int k) {
+    int row = 0, rem = k;
+    for (int s = 0; s < P.ns; ++s) {
+        const int dgt = rem % P.R[s];
+        rem /= P.R[s];
+        row += dgt * (P.NB[s] / P.R[s]);
+    }
+    return row;
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void bfly_any(cplx* v) {
+    if constexpr (R == 2 || R == 4 || R == 8 || R == 16)
+        Bfly<R, INV>::run(v);
+    else
+        bfly_direct<R, INV>(v, nullptr, 0);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void rt_stage_R(cplx* __restrict__ buf, int L, const cplx* __restrict__ tw, int N, int NB,
+                                           int TS) {
+    const int M = NB / R;
+    const int NBF = (N / NB) * M;
+    for (int w = threadIdx.x; w < NBF * L; w += blockDim.x) {
+        const int line = w % L, bf = w / L;
+        const int blk = bf / M, j = bf - blk * M;
+        cplx* base = buf + line;
+        const int row0 = blk * NB + j;
+        cplx v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = base[pidx(row0 + r * M) * L];
+        if (INV) {
+            if (M > 1 && j > 0) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, TS * q * j, true));
+            }
+            bfly_any<R, true>(v);
+        } else {
+            bfly_any<R, false>(v);
+            if (M > 1 && j > 0) {
+#pragma unroll
+                for (int q = 1; q < R; ++q) v[q] = cmul(v[q], ldtw(tw, TS * q * j, false));
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) base[pidx(row0 + r * M) * L] = v[r];
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void rt_stage(cplx* buf, int L, const cplx* tw, const RtPlan& P, int s) {
+    const int N = P.n, NB = P.NB[s], TS = P.TS[s];
+    switch (P.R[s]) {
+        case 2: rt_stage_R<2, INV>(buf, L, tw, N, NB, TS); break;
+        case 3: rt_stage_R<3, INV>(buf, L, tw, N, NB, TS); break;
+        case 4: rt_stage_R<4, INV>(buf, L, tw, N, NB, TS); break;
+        case 5: rt_stage_R<5, INV>(buf, L, tw, N, NB, TS); break;
+        case 7: rt_stage_R<7, INV>(buf, L, tw, N, NB, TS); break;
+        case 8: rt_stage_R<8, INV>(buf, L, tw, N, NB, TS); break;
+        case 9: rt_stage_R<9, INV>(buf, L, tw, N, NB, TS); break;
+        case 11: rt_stage_R<11, INV>(buf, L, tw, N, NB, TS); break;
+        case 13: rt_stage_R<13, INV>(buf, L, tw, N, NB, TS); break;
+        case 15: rt_stage_R<15, INV>(buf, L, tw, N, NB, TS); break;
+        case 16: rt_stage_R<16, INV>(buf, L, tw, N, NB, TS); break;
+        case 17: rt_stage_R<17, INV>(buf, L, tw, N, NB, TS); break;
+        case 19: rt_stage_R<19, INV>(buf, L, tw, N, NB, TS); break;
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void rt_fft_inplace(cplx* buf, int L, const cplx* tw, const RtPlan& P) {
+    if (!INV) {
+        for (int s = 0; s < P.ns; ++s) {
+            rt_stage<false>(buf, L, tw, P, s);
+            __syncthreads();
+        }
+    } else {
+        for (int s = P.ns - 1; s >= 0; --s) {
+            rt_stage<true>(buf, L, tw, P, s);
+            __syncthreads();
+        }
+    }
+}
+
+// S2 / S4
+template <int T, bool INV>
+__global__ void __launch_bounds__(256, 2) k_c2c_rt(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                 const cplx* __restrict__ tw, RtPlan P, int64_t inner, int ntile) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int N = P.n;
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t base = o * N * inner + (int64_t)tile * T;
+    for (int e0 = threadIdx.x; e0 < N * T; e0 += 4 * blockDim.x) {
+        cplx c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < N * T) c[u] = in[base + (int64_t)(e / T) * inner + (e % T)];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < N * T) {
+                const int t = e % T, row = e / T;
+                const int srow = INV ? rt_row_of_freq(P, row) : row;
+                buf[pidx(srow) * T + t] = c[u];
+            }
+        }
+    }
+    __syncthreads();
+    rt_fft_inplace<INV>(buf, T, tw, P);
+    for (int e = threadIdx.x; e < N * T; e += blockDim.x) {
+        const int t = e % T, row = e / T;
+        const int srow = INV ? row : rt_row_of_freq(P, row);
+        out[base + (int64_t)row * inner + t] = buf[pidx(srow) * T + t];
+    }
+}
+
+// S3
+template <int T, int KIND, int DIM>
+__global__ void __launch_bounds__(384) k_mid_green_rt(cplx* __restrict__ data, const cplx* __restrict__ tw, RtPlan P,
+                                                       GreenDesc g, int64_t inner, int nh, int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int L = D * T;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int N = P.n;
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    const int tot = D * N * T;
+    for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * blockDim.x) {
+        cplx c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < tot) {
+                const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+                c[u] = data[((int64_t)cc * N + row) * inner + i0 + t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = e0 + u * blockDim.x;
+            if (e < tot) {
+                const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+                buf[pidx(row) * L + cc * T + t] = c[u];
+            }
+        }
+    }
+    __syncthreads();
+    rt_fft_inplace<false>(buf, L, tw, P);
+    for (int idx = threadIdx.x; idx < N * T; idx += blockDim.x) {
+        const int row = idx / T, tt = idx - row * T;
+        int k[3];
+        k[0] = fh_freq(rt_freq_of_row(P, row), N);
+        const int64_t ii = i0 + tt;
+        bool valid = true;
+        if (DIM == 3) {
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
+            k[2] = fh_freq(i2, g.N[2]);
+            valid = i2 < nh;
+        } else {
+            k[1] = fh_freq((int)ii, g.N[1]);
+            k[2] = 0;
+            valid = (int)ii < nh;
+        }
+        cplx* sr = buf + pidx(row) * L + tt;
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * T];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) sr[cc * T] = e[cc];
+    }
+    __syncthreads();
+    rt_fft_inplace<true>(buf, L, tw, P);
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+        const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+        data[((int64_t)cc * N + row) * inner + i0 + t] = buf[pidx(row) * L + cc * T + t];
+    }
+}
+
+// S1 (any N, any number of rows: the last CTA masks rows >= nrows)
+template <int D, int TRW, int ALAY>
+__global__ void __launch_bounds__(256, 2)
+    k_fwd_last_rt(const double* __restrict__ A, const unsigned char* __restrict__ phase, const double* __restrict__ lut,
+                  const Lut2C lutc, int nphase, double* __restrict__ p, const double* __restrict__ r,
+                  const double* __restrict__ scal, int pupdate, cplx* __restrict__ spec, const cplx* __restrict__ tw,
+                  RtPlan P, int64_t nrows, int nh, int pitch) {
+    constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [npr][NP]
+    double* bd = reinterpret_cast<double*>(buf);
+    const int N = P.n;
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    const int64_t n = nrows * N;
+    const double beta = pupdate ? scal[3] : 0.0;
+    __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
+    if (ALAY == 2) {
+        for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
+        __syncthreads();
+    }
+    for (int v = threadIdx.x; v < TRW * N; v += NT) {
+        const int row = v / N, i2 = v - row * N;
+        const bool live = row0 + row < nrows;
+        const int64_t gv = (row0 + row) * N + i2;
+        int ph = 0;
+        if ((ALAY == 2 || ALAY == 3) && live) ph = phase[gv];
+        double pv[D];
+#pragma unroll
+        for (int jj = 0; jj < D; ++jj) {
+            double q = 0.0;
+            if (live) {
+                q = p[(size_t)jj * n + gv];
+                if (pupdate) {
+                    q = r[(size_t)jj * n + gv] + beta * q;
+                    p[(size_t)jj * n + gv] = q;
+                }
+            }
+            pv[jj] = q;
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double s = 0.0;
+            if (ALAY < 0) {
+                s = pv[i];
+            } else if (live) {
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) {
+                    double a;
+                    if (ALAY == 3) {
+                        a = ph ? lutc.c[1][i * D + jj] : lutc.c[0][i * D + jj];
+                    } else if (ALAY == 2) {
+                        a = slut[ph * D * D + i * D + jj];
+                    } else if (ALAY == 1) {
+                        const int lo = i < jj ? i : jj, hi = i < jj ? jj : i;
+                        a = A[((size_t)lo * D + hi) * n + gv];
+                    } else {
+                        a = A[((size_t)i * D + jj) * n + gv];
+                    }
+                    s += a * pv[jj];
+                }
+            }
+            const int Lr = i * TRW + row;
+            bd[2 * (pidx(i2) * NP + (Lr >> 1)) + (Lr & 1)] = s;
+        }
+    }
+    __syncthreads();
+    rt_fft_inplace<false>(buf, NP, tw, P);
+    for (int it = threadIdx.x; it < NL * pitch; it += NT) {
+        const int Lr = it / pitch, k = it - Lr * pitch;
+        const int c = Lr / TRW, row = Lr - c * TRW;
+        if (row0 + row >= nrows) continue;
+        cplx X = make_double2(0.0, 0.0);
+        if (k < nh) {
+            const int km = (k == 0) ? 0 : N - k;
+            const cplx a = buf[pidx(rt_row_of_freq(P, k)) * NP + (Lr >> 1)];
+            const cplx b = buf[pidx(rt_row_of_freq(P, km)) * NP + (Lr >> 1)];
+            X = (Lr & 1) ? make_double2(0.5 * (a.y + b.y), -0.5 * (a.x - b.x))
+                         : make_double2(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+        }
+        spec[((size_t)c * nrows + row0 + row) * pitch + k] = X;
+    }
+}
+
+// S5
+template <int D, int TRW>
+__global__ void __launch_bounds__(256, 2)
+    k_inv_last_rt(const cplx* __restrict__ spec, double* __restrict__ y, const double* __restrict__ pdot,
+                  double* __restrict__ part, const cplx* __restrict__ tw, RtPlan P, int64_t nrows, int nh, int pitch,
+                  double scale) {
+    constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    __shared__ double red[32];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);
+    const int N = P.n;
+    const int64_t row0 = (int64_t)blockIdx.x * TRW;
+    for (int it = threadIdx.x; it < NP * nh; it += NT) {
+        const int pr = it / nh, k = it - pr * nh;
+        const int La = 2 * pr, Lb = 2 * pr + 1;
+        const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
+        cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+        if (row0 + ra < nrows) a = spec[((size_t)ca * nrows + row0 + ra) * pitch + k];
+        if (row0 + rb < nrows) b = spec[((size_t)cb * nrows + row0 + rb) * pitch + k];
+        if (k == 0 || 2 * k == N) {
+            a.y = 0.0;
+            b.y = 0.0;
+        }
+        buf[pidx(rt_row_of_freq(P, k)) * NP + pr] = make_double2(a.x - b.y, a.y + b.x);
+        if (k > 0 && 2 * k != N) buf[pidx(rt_row_of_freq(P, N - k)) * NP + pr] = make_double2(a.x + b.y, -a.y + b.x);
+    }
+    __syncthreads();
+    rt_fft_inplace<true>(buf, NP, tw, P);
+    double acc = 0.0;
+    for (int it = threadIdx.x; it < NL * N; it += NT) {
+        const int Lr = it / N, i2 = it - Lr * N;
+        const int c = Lr / TRW, row = Lr - c * TRW;
+        if (row0 + row >= nrows) continue;
+        const cplx z = buf[pidx(i2) * NP + (Lr >> 1)];
+        const double v = ((Lr & 1) ? z.y : z.x) * scale;
+        const size_t o = ((size_t)c * nrows + row0 + row) * N + i2;
+        y[o] = v;
+        if (pdot) acc += pdot[o] * v;
+    }
+    if (pdot) {
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    }
+}

@@ -48,6 +48,8 @@ struct fh_ga {
     cplx* spec;     // [D][nrows][pitch]
     // configuration
     bool fast_last, fast_mid1, fast_mid0;
+    bool rt_ok[3];   // run-time-length in-place kernels usable on axis a (any N = up to 3 supported radices)
+    RtPlan rt[3];
     int mid_T, trw, mid_pipe;
     int chunk_cols;      // L2 blocking of S2-S3-S4: columns of the spectrum rows per chunk (0 = off)
     int cur_col0, cur_ncols;  // chunk the next S3 launch works on (0,0 = whole rows)
@@ -408,6 +410,154 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     return FH_OK;
 }
 
+// ------------------------------------------------------------------ run-time-length kernels (fh_fast.cuh, RtPlan)
+static bool make_rt_plan(const AxisDesc& ax, RtPlan& P) {
+    if (ax.nfac < 1 || ax.nfac > 3) return false;
+    P.n = ax.n;
+    P.ns = ax.nfac;
+    int nb = ax.n, ts = 1;
+    for (int s = 0; s < 3; ++s) {
+        P.R[s] = P.NB[s] = P.TS[s] = 1;
+    }
+    for (int s = 0; s < ax.nfac; ++s) {
+        const int R = ax.fac[s];
+        const bool okR = (R == 2 || R == 3 || R == 4 || R == 5 || R == 7 || R == 8 || R == 9 || R == 11 || R == 13 ||
+                          R == 15 || R == 16 || R == 17 || R == 19);
+        if (!okR) return false;
+        P.R[s] = R;
+        P.NB[s] = nb;
+        P.TS[s] = ts;
+        nb /= R;
+        ts *= R;
+    }
+    P.npr = ax.n + ax.n / 16 + 1;
+    return true;
+}
+
+static int launch_c2c_rt(fh_ga* op, int axis, cplx* data, int64_t outer, int64_t inner, bool inv) {
+    const RtPlan& P = op->rt[axis];
+    const cplx* tw = op->plan->ax[axis].tw;
+    int rc;
+    static const int wantT = env_int("FH_RT_T", 16);
+    if (wantT == 16 && inner % 16 == 0 && (size_t)P.npr * 16 * sizeof(cplx) <= (size_t)fh_max_smem_optin() / 2) {
+        constexpr int T = 16;
+        const size_t smem = (size_t)P.npr * T * sizeof(cplx);
+        const int ntile = (int)(inner / T);
+        const unsigned nblk = (unsigned)(outer * ntile);
+        if (inv) {
+            if ((rc = smem_attr(k_c2c_rt<T, true>, smem))) return rc;
+            k_c2c_rt<T, true><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, P, inner, ntile);
+        } else {
+            if ((rc = smem_attr(k_c2c_rt<T, false>, smem))) return rc;
+            k_c2c_rt<T, false><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, P, inner, ntile);
+        }
+        FH_LAUNCH_CHECK();
+        return FH_OK;
+    }
+    constexpr int T = 8;
+    const size_t smem = (size_t)P.npr * T * sizeof(cplx);
+    if (smem > (size_t)fh_max_smem_optin()) return fh_set_error(FH_ERR_UNSUPPORTED, "axis length %d too large", P.n);
+    const int ntile = (int)(inner / T);
+    const unsigned nblk = (unsigned)(outer * ntile);
+    if (inv) {
+        if ((rc = smem_attr(k_c2c_rt<T, true>, smem))) return rc;
+        k_c2c_rt<T, true><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, P, inner, ntile);
+    } else {
+        if ((rc = smem_attr(k_c2c_rt<T, false>, smem))) return rc;
+        k_c2c_rt<T, false><<<nblk, 256, smem, fh_stream()>>>(data, data, tw, P, inner, ntile);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
+template <int T, int KIND, int DIM>
+static int launch_mid_rt_T(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const fh_plan* p = op->plan;
+    const RtPlan& P = op->rt[0];
+    const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
+    const size_t smem = (size_t)P.npr * D * T * sizeof(cplx);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_rt<T, KIND, DIM>, smem))) return rc;
+    k_mid_green_rt<T, KIND, DIM><<<(unsigned)(inner / T), 384, smem, fh_stream()>>>(op->specT, p->ax[0].tw, P, op->g,
+                                                                                 inner, p->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+template <int KIND, int DIM>
+static int launch_mid_rt(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    const size_t per_line = (size_t)op->rt[0].npr * D * sizeof(cplx);
+    const size_t cap = (size_t)fh_max_smem_optin();
+    if (4 * per_line <= cap / 2 || (4 * per_line <= cap && 2 * per_line > cap / 2)) return launch_mid_rt_T<4, KIND, DIM>(op);
+    if (2 * per_line <= cap) return launch_mid_rt_T<2, KIND, DIM>(op);
+    if (per_line <= cap) return launch_mid_rt_T<1, KIND, DIM>(op);
+    return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: N0=%d D=%d does not fit shared memory", op->rt[0].n, D);
+}
+
+template <int D, int TRW, int ALAY>
+static int launch_fwd_last_rtA(fh_ga* op, double* p, const double* r, int pupdate) {
+    constexpr int NP = D * TRW / 2;
+    const fh_plan* pl = op->plan;
+    const int ax = pl->dim - 1;
+    const RtPlan& P = op->rt[ax];
+    const size_t smem = (size_t)P.npr * NP * sizeof(cplx);
+    const unsigned nblk = (unsigned)fh_ceil_div(op->nrows, TRW);
+    int rc;
+    if ((rc = smem_attr(k_fwd_last_rt<D, TRW, ALAY>, smem))) return rc;
+    k_fwd_last_rt<D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p, r,
+                                                                  op->scal, pupdate, op->spec, pl->ax[ax].tw, P,
+                                                                  op->nrows, pl->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+template <int D, int TRW>
+static int launch_fwd_last_rtD(fh_ga* op, double* p, const double* r, int pupdate) {
+    if (op->a_mode == 2 && op->nphase <= 2 && D * D <= 36) return launch_fwd_last_rtA<D, TRW, 3>(op, p, r, pupdate);
+    if (op->a_mode == 2) return launch_fwd_last_rtA<D, TRW, 2>(op, p, r, pupdate);
+    if (op->a_mode == 1) return launch_fwd_last_rtA<D, TRW, 1>(op, p, r, pupdate);
+    return launch_fwd_last_rtA<D, TRW, 0>(op, p, r, pupdate);
+}
+// rows per CTA: enough lines (D*TRW/2) to keep 256 threads busy with the few wide butterflies of an odd length,
+// falling back to the small tiles when the padded lines do not fit shared memory twice
+static bool rt_wide(const fh_ga* op, int NPwide) {
+    static const int want = env_int("FH_RT_WIDE", 1);
+    return want && (size_t)op->rt[op->plan->dim - 1].npr * NPwide * sizeof(cplx) <= (size_t)fh_max_smem_optin() / 2;
+}
+static int launch_fwd_last_rt(fh_ga* op, double* p, const double* r, int pupdate) {
+    switch (op->D) {
+        case 6: return rt_wide(op, 18) ? launch_fwd_last_rtD<6, 6>(op, p, r, pupdate) : launch_fwd_last_rtD<6, 2>(op, p, r, pupdate);
+        case 3: return rt_wide(op, 12) ? launch_fwd_last_rtD<3, 8>(op, p, r, pupdate) : launch_fwd_last_rtD<3, 4>(op, p, r, pupdate);
+        case 2: return rt_wide(op, 12) ? launch_fwd_last_rtD<2, 12>(op, p, r, pupdate) : launch_fwd_last_rtD<2, 4>(op, p, r, pupdate);
+    }
+    return fh_set_error(FH_ERR_UNSUPPORTED, "fused operator: D=%d", op->D);
+}
+template <int D, int TRW>
+static int launch_inv_last_rtD(fh_ga* op, double* y, const double* pdot, int* npart) {
+    constexpr int NP = D * TRW / 2;
+    const fh_plan* pl = op->plan;
+    const int ax = pl->dim - 1;
+    const RtPlan& P = op->rt[ax];
+    const size_t smem = (size_t)P.npr * NP * sizeof(cplx);
+    const unsigned nblk = (unsigned)fh_ceil_div(op->nrows, TRW);
+    int rc;
+    if ((rc = smem_attr(k_inv_last_rt<D, TRW>, smem))) return rc;
+    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_rt<D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[ax].tw, P, op->nrows,
+                                                            pl->nh, op->pitch, 1.0 / (double)pl->nreal);
+    FH_LAUNCH_CHECK();
+    if (npart) *npart = (int)nblk;
+    return FH_OK;
+}
+static int launch_inv_last_rt(fh_ga* op, double* y, const double* pdot, int* npart) {
+    switch (op->D) {
+        case 6: return rt_wide(op, 18) ? launch_inv_last_rtD<6, 6>(op, y, pdot, npart) : launch_inv_last_rtD<6, 2>(op, y, pdot, npart);
+        case 3: return rt_wide(op, 12) ? launch_inv_last_rtD<3, 8>(op, y, pdot, npart) : launch_inv_last_rtD<3, 4>(op, y, pdot, npart);
+        case 2: return rt_wide(op, 12) ? launch_inv_last_rtD<2, 12>(op, y, pdot, npart) : launch_inv_last_rtD<2, 4>(op, y, pdot, npart);
+    }
+    return fh_set_error(FH_ERR_UNSUPPORTED, "fused operator: D=%d", op->D);
+}
+
 template <int N, int D, int TRW, int ALAY>
 static int launch_fwd_last_g3A(fh_ga* op, double* p, const double* r, int pupdate) {
     constexpr int NP = D * TRW / 2;
@@ -558,9 +708,10 @@ static int analyse_coefficients(fh_ga* op) {
     op->phase = NULL;
     op->lut = NULL;
     op->nphase = 0;
-    if (want == 0 || !op->fast_last) return FH_OK;
+    const bool rt_last = op->rt_ok[op->plan->dim - 1];
+    if (want == 0 || !(op->fast_last || rt_last)) return FH_OK;
     const unsigned grid = (unsigned)(fh_num_sms() * 8);
-    if ((want < 0 || want == 2) && n % 2 == 0) {
+    if ((want < 0 || want == 2) && (n % 2 == 0 || !op->fast_last)) {
         unsigned long long* first = NULL;
         FH_CUDA(cudaMalloc((void**)&first, sizeof(unsigned long long)));
         FH_CUDA(cudaMalloc((void**)&op->phase, (size_t)n));
@@ -681,6 +832,18 @@ static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, i
     op->fast_last = use_fast && pow2fast(plan->N[d - 1]) && (op->nrows % op->trw == 0);
     op->fast_mid1 = use_fast && d == 3 && pow2fast(plan->N[1]);
     op->fast_mid0 = use_fast && pow2fast(plan->N[0]) && (((int64_t)op->n1l * op->pitch) % 4 == 0);
+    const int use_rt = env_int("FH_RT", 7);
+    for (int a = 0; a < 3; ++a) op->rt_ok[a] = false;
+    // FH_RT mask: bit 0 = axis 0 (S3), bit 1 = middle axis (S2/S4), bit 2 = last axis (S1/S5)
+    for (int a = 0; a < d; ++a) {
+        const int bit = (a == 0) ? 1 : (a == d - 1 ? 4 : 2);
+        op->rt_ok[a] = use_fast && (use_rt & bit) && make_rt_plan(plan->ax[a], op->rt[a]);
+    }
+    if (op->rt_ok[d - 1] && (size_t)op->rt[d - 1].npr * 6 * sizeof(cplx) > (size_t)fh_max_smem_optin()) op->rt_ok[d - 1] = false;
+    if (d == 3 && op->rt_ok[1] && (size_t)op->rt[1].npr * 8 * sizeof(cplx) > (size_t)fh_max_smem_optin()) op->rt_ok[1] = false;
+    if (op->rt_ok[0] && ((size_t)op->rt[0].npr * D * sizeof(cplx) > (size_t)fh_max_smem_optin() ||
+                         ((int64_t)op->n1l * op->pitch) % 4 != 0))
+        op->rt_ok[0] = false;
     op->mid_T = env_int("FH_MID_T", 4);
     op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
@@ -754,7 +917,10 @@ extern "C" int fh_ga_config(const fh_ga* op, int* flags, int* pitch, int* mid_T)
     FH_REQUIRE(op, "fh_ga_config: null argument");
     if (flags)
         *flags = (op->fast_last ? 1 : 0) | (op->fast_mid1 ? 2 : 0) | (op->fast_mid0 ? 4 : 0) | (op->a_mode << 4) |
-                 (op->nphase << 8);
+                 (op->nphase << 8) |
+                 ((!op->fast_last && op->rt_ok[op->plan->dim - 1]) ? 1 << 16 : 0) |
+                 ((op->plan->dim == 3 && !op->fast_mid1 && op->rt_ok[1]) ? 1 << 17 : 0) |
+                 ((!op->fast_mid0 && op->rt_ok[0]) ? 1 << 18 : 0);
     if (pitch) *pitch = op->pitch;
     if (mid_T) *mid_T = op->mid_T;
     return FH_OK;
@@ -895,6 +1061,7 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
     switch (stage) {
         case 1:
             if (op->fast_last) return launch_fwd_last_fast(op, x, r, pupdate, true);
+            if (op->rt_ok[d - 1]) return launch_fwd_last_rt(op, x, r, pupdate);
             if (pupdate) {
                 k_cg_pupdate<<<ga_grid(D * n), GA_NT, 0, fh_stream()>>>(D * n, x, r, op->scal);
                 FH_LAUNCH_CHECK();
@@ -910,12 +1077,18 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
         case 2:
             if (d != 3) return FH_OK;
             if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, false);
+            if (op->rt_ok[1]) return launch_c2c_rt(op, 1, op->spec, (int64_t)D * op->n0l, op->pitch, false);
             return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, false, 1.0);
         case 3:
             if (op->fast_mid0) {
                 if (op->g.kind == FH_GREEN_SCALAR)
                     return (d == 3) ? launch_mid_fast<FH_GREEN_SCALAR, 3>(op) : launch_mid_fast<FH_GREEN_SCALAR, 2>(op);
                 return (d == 3) ? launch_mid_fast<FH_GREEN_ELASTIC, 3>(op) : launch_mid_fast<FH_GREEN_ELASTIC, 2>(op);
+            }
+            if (op->rt_ok[0]) {
+                if (op->g.kind == FH_GREEN_SCALAR)
+                    return (d == 3) ? launch_mid_rt<FH_GREEN_SCALAR, 3>(op) : launch_mid_rt<FH_GREEN_SCALAR, 2>(op);
+                return (d == 3) ? launch_mid_rt<FH_GREEN_ELASTIC, 3>(op) : launch_mid_rt<FH_GREEN_ELASTIC, 2>(op);
             }
             if (op->g.kind == FH_GREEN_SCALAR)
                 return (d == 3) ? launch_mid_green_generic<FH_GREEN_SCALAR, 3>(op)
@@ -925,9 +1098,12 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
         case 4:
             if (d != 3) return FH_OK;
             if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, true);
+            if (op->rt_ok[1]) return launch_c2c_rt(op, 1, op->spec, (int64_t)D * op->n0l, op->pitch, true);
             return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, true, 1.0);
         case 5:
             if (op->fast_last) return launch_inv_last_fast(op, y, dot ? x : NULL, npart);
+            // measured (255^3, 243^3): the generic batched C2R beats the run-time-length one; FH_RT bit 3 opts in
+            if (op->rt_ok[d - 1] && (env_int("FH_RT", 7) & 8)) return launch_inv_last_rt(op, y, dot ? x : NULL, npart);
             if ((rc = fh_launch_c2r_last(p, op->spec, y, nlines, op->pitch, 1.0 / (double)p->nreal))) return rc;
             if (dot) {
                 const unsigned g = ga_grid(D * n);

@@ -203,7 +203,13 @@ cases = [((6, 5), (1.0, 2.0), 0, (0, 0, 0, 1, 0, 0)), ((5, 5), (1.0, 1.0), 1, (0
          ((512, 16, 32), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((16, 512, 64), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0)),
          ((32, 32, 1024), (1, 1, 2), 1, (0, 1, -1, 1, 0, 0)), ((2048, 16, 16), (1, 1, 1), 0, (0, 1, 0, -1, 0, 0)),
          ((512, 512), (1, 1), 1, (0, 0, 1, -1, 0, 0)), ((1024, 32), (1, 1), 0, (0, 0, 0, 1, 0, 0)),
-         ((32, 16), (1, 1), 1, (0, 0, 1, -1, 0, 0))]
+         ((32, 16), (1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         # run-time-length kernels (odd / mixed radices), incl. an axis that falls back
+         ((15, 15, 15), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((45, 35, 63), (1, 2, 1), 0, (0, 1, 0, -1, 0, 0)),
+         ((255, 15, 51), (1, 1, 1), 1, (0, 1, -1, 1, 0, 0)), ((6, 10, 12), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         ((27, 25, 49), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0)), ((255, 255), (1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         ((99, 143), (1, 1), 0, (0, 0, 0, 1, 0, 0)), ((23, 29, 31), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         ((85, 64, 57), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((3, 5, 7), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0))]
 for N, Y, kind, coef in cases:
     d = len(N)
     D = d if kind == 0 else d*(d+1)//2
