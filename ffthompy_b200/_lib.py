@@ -76,6 +76,12 @@ _SIGNATURES = {
                                   c_int]),
     'fh_ga_buffers': (c_int, [c_vp, C.POINTER(c_vp), C.POINTER(c_vp), p_int]),
     'fh_ga_last_dot': (c_int, [c_vp, p_dbl]),
+    'fh_ga_slab_direct': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    'fh_ga_slab_stage': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    'fh_cgd_init': (c_int, [c_vp, c_vp, c_vp]),
+    'fh_cgd_update': (c_int, [c_vp, c_vp, c_vp]),
+    'fh_cgd_local_sum': (c_int, [c_vp, c_vp]),
+    'fh_cgd_scal': (c_int, [c_vp, c_vp, c_int, p_dbl]),
     'fh_cg_xr_update': (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, p_dbl]),
     'fh_cg_p_update': (c_int, [c_i64, c_vp, c_vp, c_dbl]),
     'fh_ga_destroy': (c_int, [c_vp]),

@@ -754,7 +754,22 @@ template <>
 struct Fac3<2048> {
     static constexpr int Ra = 8, Rb = 16, Rc = 16;
 };
+// 64/128/256 have dedicated register-resident kernels for the single-GPU pipeline; these three-stage
+// splits serve the slab-exchange kernels (k_c2c_map / k_mid_green_map), which exist in this family only
+template <>
+struct Fac3<64> {
+    static constexpr int Ra = 4, Rb = 4, Rc = 4;
+};
+template <>
+struct Fac3<128> {
+    static constexpr int Ra = 8, Rb = 4, Rc = 4;
+};
+template <>
+struct Fac3<256> {
+    static constexpr int Ra = 8, Rb = 8, Rc = 4;
+};
 static inline bool fh_gen3_len(int n) { return n == 16 || n == 32 || n == 512 || n == 1024 || n == 2048; }
+static inline bool fh_map_len(int n) { return fh_gen3_len(n) || n == 64 || n == 128 || n == 256; }
 
 template <int N>
 __host__ __device__ __forceinline__ int smem_freq_of_row(int row) {
@@ -1331,5 +1346,123 @@ __global__ void __launch_bounds__(256, 2)
     if (pdot) {
         acc = block_sum(acc, red);
         if (threadIdx.x == 0) part[blockIdx.x] = acc;
+    }
+}
+
+
+// ------------------------------------------------------------------ slab-exchange addressing
+// The multi-GPU pipeline moves the half spectrum between x-slabs and y-slabs with all-to-all.  So that
+// no pack/unpack pass is needed, the strided-axis kernels address the exchange buffers directly: a
+// line (panel o, row, column t) lives at  base(o) + rowoff(row) + t.
+struct LineMap {
+    const int64_t* off;        // per-row offsets (nullptr: row * rstride)
+    int64_t rstride;
+    int64_t cstride, istride;  // panel o = c * nper + i  ->  c * cstride + i * istride
+    int nper;
+};
+__device__ __forceinline__ int64_t linemap_base(const LineMap& m, int64_t o) {
+    const int64_t c = o / m.nper, i = o - c * m.nper;
+    return c * m.cstride + i * m.istride;
+}
+__device__ __forceinline__ int64_t linemap_row(const LineMap& m, int row) {
+    return m.off ? m.off[row] : (int64_t)row * m.rstride;
+}
+
+// S2 / S4 between the natural x-slab spectrum and an exchange buffer (out of place)
+template <int N, int T, bool INV>
+__global__ void __launch_bounds__(256) k_c2c_map(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                  const cplx* __restrict__ tw, LineMap mi, LineMap mo, int ntile) {
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][T]
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t bi = linemap_base(mi, o) + (int64_t)tile * T;
+    const int64_t bo = linemap_base(mo, o) + (int64_t)tile * T;
+    constexpr int U = 4, NT = 256;
+    for (int e0 = threadIdx.x; e0 < N * T; e0 += U * NT) {
+        cplx c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < N * T) c[u] = in[bi + linemap_row(mi, e / T) + (e % T)];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < N * T) {
+                const int t = e % T, row = e / T;
+                const int srow = INV ? smem_row_of_freq<N>(row) : row;
+                buf[pidx(srow) * T + t] = c[u];
+            }
+        }
+    }
+    __syncthreads();
+    smem_fft_inplace<N, INV>(buf, T, tw);
+    for (int e = threadIdx.x; e < N * T; e += NT) {
+        const int t = e % T, row = e / T;
+        const int srow = INV ? row : smem_row_of_freq<N>(row);
+        out[bo + linemap_row(mo, row) + t] = buf[pidx(srow) * T + t];
+    }
+}
+
+// S3 in place on an exchange buffer: element (c, row, ii) at rowoff[row] + c * cstride + ii
+template <int N, int T, int KIND, int DIM>
+__global__ void __launch_bounds__(384) k_mid_green_map(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g,
+                                                        const int64_t* __restrict__ rowoff, int64_t cstride, int nh,
+                                                        int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int L = D * T, NT = 384, U = 4;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][D*T]
+    const int64_t i0 = (int64_t)blockIdx.x * T;
+    constexpr int TOT = D * N * T;
+    for (int e0 = threadIdx.x; e0 < TOT; e0 += U * NT) {
+        cplx c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+                c[u] = data[rowoff[row] + (int64_t)cc * cstride + i0 + t];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+                buf[pidx(row) * L + cc * T + t] = c[u];
+            }
+        }
+    }
+    __syncthreads();
+    smem_fft_inplace<N, false>(buf, L, tw);
+    for (int idx = threadIdx.x; idx < N * T; idx += NT) {
+        const int row = idx / T, tt = idx - row * T;
+        int k[3];
+        k[0] = fh_freq(smem_freq_of_row<N>(row), N);
+        const int64_t ii = i0 + tt;
+        const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+        k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
+        k[2] = fh_freq(i2, g.N[2]);
+        const bool valid = i2 < nh;
+        cplx* sr = buf + pidx(row) * L + tt;
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * T];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) sr[cc * T] = e[cc];
+    }
+    __syncthreads();
+    smem_fft_inplace<N, true>(buf, L, tw);
+    for (int e = threadIdx.x; e < TOT; e += NT) {
+        const int t = e % T, row = (e / T) % N, cc = e / (T * N);
+        data[rowoff[row] + (int64_t)cc * cstride + i0 + t] = buf[pidx(row) * L + cc * T + t];
     }
 }

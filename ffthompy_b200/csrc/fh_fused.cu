@@ -61,7 +61,33 @@ struct fh_ga {
     int64_t kit;
     int have_beta;
     int last_npart;  // partial sums left in `part` by the last stage-5 launch
+    // row range of the next S1 / S5 launch (chunked slab pipeline); row_cnt = 0 means all rows
+    int64_t row_beg, row_cnt;
+    // zero-copy slab exchange (fh_ga_slab_direct): chunk-major blocks [J][G][D][n0c][n1l][pitch]
+    int sd_world, sd_nchunk, sd_n0c;
+    cplx* sd_bufA;      // S2 output / S4 input (send buffer forward, receive buffer backward)
+    cplx* sd_bufB;      // S3 in place (receive buffer forward, send buffer backward)
+    int64_t* sd_off1;   // [N1] row offsets of the axis-1 passes inside one chunk of bufA
+    int64_t* sd_off0;   // [N0] row offsets of the axis-0 pass inside bufB
 };
+
+// rows handled by the next S1 / S5 launch: element offsets into fields (ro) and spectrum rows (so),
+// CTA count and first partial-sum slot
+struct RowRange {
+    int64_t ro, so;
+    unsigned nblk, pb;
+};
+static RowRange row_range(const fh_ga* op, int TRW, bool round_up) {
+    const int nlast = op->plan->N[op->plan->dim - 1];
+    const int64_t beg = op->row_cnt ? op->row_beg : 0;
+    const int64_t cnt = op->row_cnt ? op->row_cnt : op->nrows;
+    RowRange rr;
+    rr.ro = beg * nlast;
+    rr.so = beg * op->pitch;
+    rr.nblk = (unsigned)(round_up ? fh_ceil_div(cnt, TRW) : cnt / TRW);
+    rr.pb = (unsigned)(beg / TRW);
+    return rr;
+}
 
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
@@ -370,13 +396,15 @@ template <int N, int D, int TRW, int ALAY>
 static int launch_fwd_last_NTA(fh_ga* op, double* p, const double* r, int pupdate) {
     constexpr int NP = D * TRW / 2, NPAD = N + N / 16;
     const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
-    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const RowRange rr_ = row_range(op, TRW, false);
+    const unsigned nblk = rr_.nblk;
     const int nt = NP * FastCfg<N>::TPL;
     const fh_plan* pl = op->plan;
     int rc;
     if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, ALAY>, smem))) return rc;
-    k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p, r,
-                                                                       op->scal, pupdate, op->spec,
+    k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(
+        op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so,
                                                                        pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
                                                                        op->pitch);
     FH_LAUNCH_CHECK();
@@ -396,17 +424,18 @@ template <int N, int D, int TRW>
 static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npart) {
     constexpr int NP = D * TRW / 2, NPAD = N + N / 16;
     const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
-    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const RowRange rr_ = row_range(op, TRW, false);
+    const unsigned nblk = rr_.nblk;
     const int nt = NP * FastCfg<N>::TPL;
     const fh_plan* pl = op->plan;
     int rc;
     if ((rc = smem_attr(k_inv_last_fast<N, D, TRW>, smem))) return rc;
-    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
-    k_inv_last_fast<N, D, TRW><<<nblk, nt, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[pl->dim - 1].tw,
+    if (pdot && rr_.pb + nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_fast<N, D, TRW><<<nblk, nt, smem, fh_stream()>>>(op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
                                                                 op->nrows, pl->nh, op->pitch,
                                                                 1.0 / (double)pl->nreal);
     FH_LAUNCH_CHECK();
-    if (npart) *npart = (int)nblk;
+    if (npart) *npart = (int)(rr_.pb + nblk);
     return FH_OK;
 }
 
@@ -502,11 +531,13 @@ static int launch_fwd_last_rtA(fh_ga* op, double* p, const double* r, int pupdat
     const int ax = pl->dim - 1;
     const RtPlan& P = op->rt[ax];
     const size_t smem = (size_t)P.npr * NP * sizeof(cplx);
-    const unsigned nblk = (unsigned)fh_ceil_div(op->nrows, TRW);
+    const RowRange rr_ = row_range(op, TRW, true);
+    const unsigned nblk = rr_.nblk;
     int rc;
     if ((rc = smem_attr(k_fwd_last_rt<D, TRW, ALAY>, smem))) return rc;
-    k_fwd_last_rt<D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p, r,
-                                                                  op->scal, pupdate, op->spec, pl->ax[ax].tw, P,
+    k_fwd_last_rt<D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(
+        op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so, pl->ax[ax].tw, P,
                                                                   op->nrows, pl->nh, op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
@@ -539,14 +570,15 @@ static int launch_inv_last_rtD(fh_ga* op, double* y, const double* pdot, int* np
     const int ax = pl->dim - 1;
     const RtPlan& P = op->rt[ax];
     const size_t smem = (size_t)P.npr * NP * sizeof(cplx);
-    const unsigned nblk = (unsigned)fh_ceil_div(op->nrows, TRW);
+    const RowRange rr_ = row_range(op, TRW, true);
+    const unsigned nblk = rr_.nblk;
     int rc;
     if ((rc = smem_attr(k_inv_last_rt<D, TRW>, smem))) return rc;
-    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
-    k_inv_last_rt<D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[ax].tw, P, op->nrows,
+    if (pdot && rr_.pb + nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_rt<D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[ax].tw, P, op->nrows,
                                                             pl->nh, op->pitch, 1.0 / (double)pl->nreal);
     FH_LAUNCH_CHECK();
-    if (npart) *npart = (int)nblk;
+    if (npart) *npart = (int)(rr_.pb + nblk);
     return FH_OK;
 }
 static int launch_inv_last_rt(fh_ga* op, double* y, const double* pdot, int* npart) {
@@ -562,12 +594,14 @@ template <int N, int D, int TRW, int ALAY>
 static int launch_fwd_last_g3A(fh_ga* op, double* p, const double* r, int pupdate) {
     constexpr int NP = D * TRW / 2;
     const size_t smem = (size_t)(N + N / 16) * NP * sizeof(cplx);
-    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const RowRange rr_ = row_range(op, TRW, false);
+    const unsigned nblk = rr_.nblk;
     const fh_plan* pl = op->plan;
     int rc;
     if ((rc = smem_attr(k_fwd_last_gen3<N, D, TRW, ALAY>, smem))) return rc;
-    k_fwd_last_gen3<N, D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(op->A, op->phase, op->lut, op->lutc, op->nphase, p,
-                                                                       r, op->scal, pupdate, op->spec,
+    k_fwd_last_gen3<N, D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(
+        op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so,
                                                                        pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
                                                                        op->pitch);
     FH_LAUNCH_CHECK();
@@ -585,15 +619,16 @@ template <int N, int D, int TRW>
 static int launch_inv_last_g3(fh_ga* op, double* y, const double* pdot, int* npart) {
     constexpr int NP = D * TRW / 2;
     const size_t smem = (size_t)(N + N / 16) * NP * sizeof(cplx);
-    const unsigned nblk = (unsigned)(op->nrows / TRW);
+    const RowRange rr_ = row_range(op, TRW, false);
+    const unsigned nblk = rr_.nblk;
     const fh_plan* pl = op->plan;
     int rc;
     if ((rc = smem_attr(k_inv_last_gen3<N, D, TRW>, smem))) return rc;
-    if (pdot && nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
-    k_inv_last_gen3<N, D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec, y, pdot, op->part, pl->ax[pl->dim - 1].tw,
+    if (pdot && rr_.pb + nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    k_inv_last_gen3<N, D, TRW><<<nblk, 256, smem, fh_stream()>>>(op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
                                                                  op->nrows, pl->nh, op->pitch, 1.0 / (double)pl->nreal);
     FH_LAUNCH_CHECK();
-    if (npart) *npart = (int)nblk;
+    if (npart) *npart = (int)(rr_.pb + nblk);
     return FH_OK;
 }
 
@@ -905,6 +940,7 @@ extern "C" int fh_ga_destroy(fh_ga* op) {
     if (!op) return FH_OK;
     if (op->phase) cudaFree(op->phase);
     if (op->lut) cudaFree(op->lut);
+    if (op->sd_off1) cudaFree(op->sd_off1);
     cudaFree(op->scal);
     cudaFreeHost(op->pinned);
     free(op);
@@ -1191,6 +1227,218 @@ static int read_norm(fh_ga* op, double* out) {
     *out = op->pinned[0];
     return FH_OK;
 }
+
+// ------------------------------------------------------------------ zero-copy, chunked slab pipeline
+// Exchange buffers are chunk-major: chunk j (x-planes [j*n0c, (j+1)*n0c) of every rank) is one contiguous
+// block [G][D][n0c][n1l][pitch] — on the x-slab side G indexes the peer that owns the k1 range, on the
+// y-slab side the peer that owns the x-planes — so one all_to_all_single per chunk moves it with no
+// pack/unpack pass, and chunk j's exchange overlaps the transforms of chunk j+1 (ffthompy_b200/slab.py).
+template <int N, int T>
+static int launch_c2c_map_NT(const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
+                             int64_t panels, int pitch, bool inv) {
+    const size_t smem = (size_t)(N + N / 16) * T * sizeof(cplx);
+    const int ntile = pitch / T;
+    const unsigned nblk = (unsigned)(panels * ntile);
+    int rc;
+    if (inv) {
+        if ((rc = smem_attr(k_c2c_map<N, T, true>, smem))) return rc;
+        k_c2c_map<N, T, true><<<nblk, 256, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+    } else {
+        if ((rc = smem_attr(k_c2c_map<N, T, false>, smem))) return rc;
+        k_c2c_map<N, T, false><<<nblk, 256, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+static int launch_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
+                          int64_t panels, int pitch, bool inv) {
+    switch (N) {
+        case 16: return launch_c2c_map_NT<16, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 32: return launch_c2c_map_NT<32, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 64: return launch_c2c_map_NT<64, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 128: return launch_c2c_map_NT<128, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 256: return launch_c2c_map_NT<256, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 512: return launch_c2c_map_NT<512, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 1024: return launch_c2c_map_NT<1024, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+        case 2048: return launch_c2c_map_NT<2048, 4>(tw, in, out, mi, mo, panels, pitch, inv);
+    }
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no slab-exchange kernel for N1=%d", N);
+}
+template <int N, int T, int KIND>
+static int launch_mid_map_NT(fh_ga* op) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? 3 : 6;
+    const fh_plan* p = op->plan;
+    const int64_t inner = (int64_t)op->n1l * op->pitch;
+    const size_t smem = (size_t)(N + N / 16) * D * T * sizeof(cplx);
+    if (smem > (size_t)fh_max_smem_optin())
+        return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: N0=%d D=%d does not fit shared memory", N, D);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_map<N, T, KIND, 3>, smem))) return rc;
+    k_mid_green_map<N, T, KIND, 3><<<(unsigned)(inner / T), 384, smem, fh_stream()>>>(
+        op->sd_bufB, p->ax[0].tw, op->g, op->sd_off0, (int64_t)op->sd_n0c * inner, p->nh, op->pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+template <int KIND>
+static int launch_mid_map(fh_ga* op) {
+    switch (op->plan->N[0]) {
+        case 16: return launch_mid_map_NT<16, 4, KIND>(op);
+        case 32: return launch_mid_map_NT<32, 4, KIND>(op);
+        case 64: return launch_mid_map_NT<64, 4, KIND>(op);
+        case 128: return launch_mid_map_NT<128, 4, KIND>(op);
+        case 256: return launch_mid_map_NT<256, 4, KIND>(op);
+        case 512: return launch_mid_map_NT<512, 2, KIND>(op);
+        case 1024: return launch_mid_map_NT<1024, 2, KIND>(op);
+        case 2048: return launch_mid_map_NT<2048, 1, KIND>(op);
+    }
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no slab-exchange kernel for N0=%d", op->plan->N[0]);
+}
+
+extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, void* bufB) {
+    FH_REQUIRE(op && bufA && bufB && bufA != bufB, "fh_ga_slab_direct: null or aliased buffers");
+    const fh_plan* p = op->plan;
+    FH_REQUIRE(p->dim == 3 && world >= 1 && nchunk >= 1, "fh_ga_slab_direct: a 3-D slab operator is required");
+    FH_REQUIRE((int64_t)op->n0l * world == p->N[0] && (int64_t)op->n1l * world == p->N[1],
+               "fh_ga_slab_direct: slab extents do not match world=%d", world);
+    FH_REQUIRE(op->n0l % nchunk == 0, "fh_ga_slab_direct: %d local planes do not split into %d chunks", op->n0l, nchunk);
+    FH_REQUIRE(((uintptr_t)bufA & 15) == 0 && ((uintptr_t)bufB & 15) == 0, "fh_ga_slab_direct: buffers must be 16-byte aligned");
+    if (!fh_map_len(p->N[0]) || !fh_map_len(p->N[1]))
+        return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_direct: N0=%d, N1=%d not in the slab-exchange kernel family",
+                            p->N[0], p->N[1]);
+    const int n0c = op->n0l / nchunk;
+    const int64_t rows_c = (int64_t)n0c * p->N[1];
+    if (nchunk > 1) {
+        const bool rt_last = !op->fast_last && op->rt_ok[2];
+        if (!(op->fast_last && rows_c % op->trw == 0) && !(rt_last && rows_c % 24 == 0))
+            return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_direct: the last-axis kernels cannot run %lld-row chunks",
+                                (long long)rows_c);
+    }
+    const int D = op->D, P = op->pitch, n1l = op->n1l, n0l = op->n0l;
+    const int64_t inner = (int64_t)n1l * P;
+    int64_t* h1 = (int64_t*)malloc(sizeof(int64_t) * p->N[1]);
+    int64_t* h0 = (int64_t*)malloc(sizeof(int64_t) * p->N[0]);
+    if (!h1 || !h0) {
+        free(h1);
+        free(h0);
+        return fh_set_error(FH_ERR_ALLOC, "fh_ga_slab_direct: out of host memory");
+    }
+    for (int k1 = 0; k1 < p->N[1]; ++k1) h1[k1] = (int64_t)(k1 / n1l) * D * n0c * inner + (int64_t)(k1 % n1l) * P;
+    for (int i0 = 0; i0 < p->N[0]; ++i0) {
+        const int g = i0 / n0l, rem = i0 % n0l, j = rem / n0c, i0c = rem % n0c;
+        h0[i0] = ((int64_t)(j * world + g) * D) * n0c * inner + (int64_t)i0c * inner;
+    }
+    if (op->sd_off1) cudaFree(op->sd_off1);
+    op->sd_off1 = op->sd_off0 = NULL;
+    cudaError_t e = cudaMalloc((void**)&op->sd_off1, sizeof(int64_t) * (p->N[0] + p->N[1]));
+    if (e == cudaSuccess) {
+        op->sd_off0 = op->sd_off1 + p->N[1];
+        e = cudaMemcpy(op->sd_off1, h1, sizeof(int64_t) * p->N[1], cudaMemcpyHostToDevice);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(op->sd_off0, h0, sizeof(int64_t) * p->N[0], cudaMemcpyHostToDevice);
+    free(h1);
+    free(h0);
+    if (e != cudaSuccess) return fh_set_error(FH_ERR_CUDA, "fh_ga_slab_direct: %s", cudaGetErrorString(e));
+    op->sd_world = world;
+    op->sd_nchunk = nchunk;
+    op->sd_n0c = n0c;
+    op->sd_bufA = (cplx*)bufA;
+    op->sd_bufB = (cplx*)bufB;
+    // padding columns travel with the rows: keep them zero
+    const size_t bytes = sizeof(cplx) * (size_t)D * n0l * p->N[1] * P;
+    FH_CUDA(cudaMemsetAsync(bufA, 0, bytes, fh_stream()));
+    FH_CUDA(cudaMemsetAsync(bufB, 0, bytes, fh_stream()));
+    return FH_OK;
+}
+
+// One step of the slab pipeline.  Without fh_ga_slab_direct: `stage` = 1..5 is the plain pipeline stage
+// (the caller packs/unpacks around its exchange), `chunk` is ignored.  With it:
+//   stage 1: S1 (sigma = A p, with p = r + beta p when pupdate) + S2 of chunk -> exchange buffer A
+//   stage 3: S3 in place on exchange buffer B (all chunks)
+//   stage 4: S4 of chunk from exchange buffer A + S5 (y rows of the chunk, partial sums of <p, y>)
+extern "C" int fh_ga_slab_stage(fh_ga* op, int stage, int chunk, double* p, const double* r, int pupdate, double* y) {
+    FH_REQUIRE(op && p && y, "fh_ga_slab_stage: null argument");
+    int np = 0, rc;
+    if (!op->sd_world) {
+        rc = ga_stage(op, stage, p, r, pupdate, y, 1, &np);
+        if (stage == 5 && !rc) op->last_npart = np;
+        return rc;
+    }
+    const fh_plan* pl = op->plan;
+    const int D = op->D, P = op->pitch, N1 = pl->N[1], n0c = op->sd_n0c;
+    FH_REQUIRE(chunk >= 0 && chunk < op->sd_nchunk, "fh_ga_slab_stage: chunk %d out of range", chunk);
+    const int64_t inner = (int64_t)op->n1l * P;
+    const int64_t chunk_elems = (int64_t)op->sd_world * D * n0c * inner;
+    const LineMap nat = {NULL, (int64_t)P, (int64_t)op->n0l * N1 * P, (int64_t)N1 * P, n0c};
+    const LineMap blk = {op->sd_off1, 0, (int64_t)n0c * inner, inner, n0c};
+    cplx* spec_c = op->spec + (size_t)chunk * n0c * N1 * P;
+    cplx* bufA_c = op->sd_bufA + (size_t)chunk * chunk_elems;
+    if (op->sd_nchunk > 1) {
+        op->row_beg = (int64_t)chunk * n0c * N1;
+        op->row_cnt = (int64_t)n0c * N1;
+    }
+    rc = FH_OK;
+    if (stage == 1) {
+        rc = ga_stage(op, 1, p, r, pupdate, y, 0, NULL);
+        if (!rc) rc = launch_c2c_map(N1, pl->ax[1].tw, spec_c, bufA_c, nat, blk, (int64_t)D * n0c, P, false);
+    } else if (stage == 3) {
+        rc = (op->g.kind == FH_GREEN_SCALAR) ? launch_mid_map<FH_GREEN_SCALAR>(op) : launch_mid_map<FH_GREEN_ELASTIC>(op);
+        op->last_npart = 0;
+    } else if (stage == 4) {
+        rc = launch_c2c_map(N1, pl->ax[1].tw, bufA_c, spec_c, blk, nat, (int64_t)D * n0c, P, true);
+        if (!rc) rc = ga_stage(op, 5, p, NULL, 0, y, 1, &np);
+        if (!rc && np > op->last_npart) op->last_npart = np;
+    } else {
+        rc = fh_set_error(FH_ERR_ARG, "fh_ga_slab_stage: stage %d (1, 3 or 4 with direct exchange buffers)", stage);
+    }
+    op->row_beg = op->row_cnt = 0;
+    return rc;
+}
+
+// Pieces of the CG iteration for a solve distributed over ranks (general/solver.py:113-136): every scalar
+// is a local partial sum -> caller's all-reduce on the device -> fh_cgd_scal.  vecs = [r | p | Ap].
+extern "C" int fh_cgd_init(fh_ga* op, const double* B, double* vecs) {
+    FH_REQUIRE(op && B && vecs, "fh_cgd_init: null argument");
+    const int64_t n = (int64_t)op->D * op->nloc;
+    const unsigned g = ga_grid(n);
+    k_cg_init<<<g, GA_NT, 0, fh_stream()>>>(n, B, vecs + 2 * n, vecs, vecs + n, op->part);
+    FH_LAUNCH_CHECK();
+    op->last_npart = (int)g;
+    return FH_OK;
+}
+extern "C" int fh_cgd_update(fh_ga* op, double* x, double* vecs) {
+    FH_REQUIRE(op && x && vecs, "fh_cgd_update: null argument");
+    const int64_t n = (int64_t)op->D * op->nloc;
+    double* r = vecs;
+    const double* p = vecs + n;
+    const double* Ap = vecs + 2 * n;
+    const unsigned g = ga_grid(n / 2 + 1);
+    if (n % 2 == 0 && (((uintptr_t)x | (uintptr_t)vecs) & 15) == 0)
+        k_cg_update<<<g, GA_NT, 0, fh_stream()>>>(n / 2, (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap,
+                                                  op->scal, op->part);
+    else
+        k_cg_update1<<<g, GA_NT, 0, fh_stream()>>>(n, x, r, p, Ap, op->scal, op->part);
+    FH_LAUNCH_CHECK();
+    op->last_npart = (int)g;
+    return FH_OK;
+}
+// sum_dev[0] = this rank's sum of the partial sums left by the last S5 / init / update launch
+extern "C" int fh_cgd_local_sum(fh_ga* op, double* sum_dev) {
+    FH_REQUIRE(op && sum_dev, "fh_cgd_local_sum: null argument");
+    FH_REQUIRE(op->last_npart > 0, "fh_cgd_local_sum: no partial sums available");
+    k_sum_part<<<1, GA_NT, 0, fh_stream()>>>(op->last_npart, op->part, sum_dev);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+// mode 0: rr, norm | mode 1: pAp, alpha | mode 2: beta, rr, norm  from the GLOBAL sum in sum_dev[0];
+// norm_host (optional) receives ||r|| (8-byte read-back, synchronises)
+extern "C" int fh_cgd_scal(fh_ga* op, const double* sum_dev, int mode, double* norm_host) {
+    FH_REQUIRE(op && sum_dev && mode >= 0 && mode <= 2, "fh_cgd_scal: bad argument");
+    k_cg_scal<<<1, GA_NT, 0, fh_stream()>>>(1, sum_dev, op->scal, 1.0 / (double)op->plan->nreal, mode);
+    FH_LAUNCH_CHECK();
+    if (norm_host) return read_norm(op, norm_host);
+    return FH_OK;
+}
+
 
 // vecs = [r | p | Ap], each D*prod(N) doubles.
 // fh_cg_begin: Ax = Afun(x0); R = B - Ax; P = R; rr = <R,R>      (solver.py:113-120)

@@ -8,10 +8,16 @@ operator application is
     S3      local (C2C axis 0, G^ with global (k0,k1,k2), inverse axis 0)
     all-to-all back
     S4, S5  local
-and CG reduces its two scalars per iteration with all-reduce.  The exchange helpers are plain
-tensor plumbing (pack, all_to_all_single, unpack) and run on any backend — tests/test_gloo_slab.py
-drives them on CPU with gloo; the transforms themselves are the CUDA kernels of the C ABI
-(fh_ga_create_slab / fh_ga_stage).
+and CG reduces its two scalars per iteration with all-reduce (device tensors, no host round trip).
+
+Two exchange modes:
+* direct (default when N0, N1 are powers of two 16..2048): the exchange buffers are chunk-major blocks
+  [J][G][D][n0l/J][n1l][pitch] that the axis-1 / axis-0 kernels address in place (fh_ga_slab_direct), so
+  an exchange is ONE all_to_all_single per chunk with no pack/unpack pass, issued asynchronously:
+  chunk j travels over NVLink while S1+S2 of chunk j+1 (forward) or S4+S5 of chunk j-1 (backward) run.
+  `direct_offsets` states the block layout; tests/test_gloo_slab.py checks it on CPU with gloo.
+* packed (any sizes): pack, all_to_all_single, unpack around the natural-layout kernels.
+The transforms themselves are the CUDA kernels of the C ABI (fh_ga_create_slab / fh_ga_slab_stage).
 """
 import ctypes as C
 
@@ -74,11 +80,35 @@ def allreduce_sum(value, device, group=None):
     return float(t.item())
 
 
+def direct_offsets(layout, D, P, nchunk):
+    """Element offsets of the chunk-major exchange blocks (mirrors fh_ga_slab_direct in csrc/fh_fused.cu).
+
+    Returns (off1, off0, cstride1, istride1, cstride0, chunk_elems):
+      x-slab side, chunk j, panel (c, i0c), row k1, column t:
+          j*chunk_elems + c*cstride1 + i0c*istride1 + off1[k1] + t
+      y-slab side, component c, global plane i0, inner index ii in [0, n1l*P):
+          off0[i0] + c*cstride0 + ii
+    """
+    G, n0l, n1l = layout.world, layout.n0l, layout.n1l
+    assert n0l % nchunk == 0
+    n0c = n0l//nchunk
+    inner = n1l*P
+    k1 = np.arange(layout.N[1])
+    off1 = (k1//n1l)*D*n0c*inner+(k1 % n1l)*P
+    i0 = np.arange(layout.N[0])
+    g, rem = i0//n0l, i0 % n0l
+    j, i0c = rem//n0c, rem % n0c
+    off0 = ((j*G+g)*D)*n0c*inner+i0c*inner
+    return off1, off0, n0c*inner, inner, n0c*inner, G*D*n0c*inner
+
+
 class SlabGA(object):
     """y = F^-1 G^ F (A x) on slab-decomposed fields, and the CG loop of general/solver.py:80-139
-    over it.  `A_local`: device tensor [D][D][n0l][N1][N2]; `G`: lazy GreenTensor on the GLOBAL grid."""
+    over it.  `A_local`: device tensor [D][D][n0l][N1][N2]; `G`: lazy GreenTensor on the GLOBAL grid.
+    `direct`: None = zero-copy chunked exchange when the kernels support the grid, True = require it,
+    False = packed exchange; `nchunk`: x-plane chunks per exchange (default: up to 4)."""
 
-    def __init__(self, A_local, G, N, group=None):
+    def __init__(self, A_local, G, N, group=None, direct=None, nchunk=None):
         import torch
         import torch.distributed as dist
         from . import _lib as L
@@ -111,6 +141,25 @@ class SlabGA(object):
         self.nloc = lay.n0l*lay.N[1]*lay.N[2]
         self.pN = float(np.prod(lay.N))
         self.exchanged_bytes = 0
+        self.sums = dev.zeros((2,))
+        # exchange mode
+        self.direct, self.nchunk = False, 1
+        if direct is not False:
+            cands = [int(nchunk)] if nchunk else [j for j in (4, 2, 1) if lay.n0l % j == 0]
+            nel = D*lay.n0l*lay.N[1]*P
+            bufA = torch.zeros(nel, dtype=torch.complex128, device=dev.device())
+            # the y-slab workspace doubles as exchange buffer B (on one rank it aliases the x-slab spectrum)
+            bufB = self.specT.reshape(-1) if world > 1 else torch.zeros_like(bufA)
+            for J in cands:
+                rc = lib.fh_ga_slab_direct(self.handle, world, J, dev.ptr(bufA), dev.ptr(bufB))
+                if rc == 0:
+                    self.direct, self.nchunk = True, J
+                    self.bufA, self.bufB = bufA.view(J, -1), bufB.view(J, -1)
+                    break
+            if not self.direct:
+                del bufA
+                if direct is True:
+                    L.check(rc)
 
     def __del__(self):
         try:
@@ -119,24 +168,52 @@ class SlabGA(object):
         except Exception:
             pass
 
-    def _stage(self, s, x, y):
-        self.L.check(self.dev.lib().fh_ga_stage(self.handle, s, self.dev.ptr(x), self.dev.ptr(y)))
+    def _stage(self, s, chunk, p, r, pupdate, y):
+        self.L.check(self.dev.lib().fh_ga_slab_stage(self.handle, s, chunk, self.dev.ptr(p),
+                                                     self.dev.ptr(r) if r is not None else None, int(pupdate),
+                                                     self.dev.ptr(y)))
 
-    def apply(self, x, y=None):
-        """x, y: device tensors [D][n0l][N1][N2] (this rank's slab)."""
+    def _a2a(self, dst, src):
+        """one exchange block; returns a work handle (None on a single rank)"""
+        import torch.distributed as dist
+        if self.layout.world == 1:
+            dst.copy_(src)
+            return None
+        self.exchanged_bytes += src.numel()*16*(self.layout.world-1)//self.layout.world
+        return dist.all_to_all_single(dst, src, group=self.group, async_op=True)
+
+    def apply(self, x, y=None, r=None, pupdate=0):
+        """x, y: device tensors [D][n0l][N1][N2] (this rank's slab).  With `pupdate` the CG direction
+        update x <- r + beta*x (beta on the device) is folded into S1, as in fh_cg_steps."""
         if y is None:
             y = self.dev.empty(x.shape)
-        self._stage(1, x, y)
-        self._stage(2, x, y)
+        if self.direct:
+            J = self.nchunk
+            works = []
+            for j in range(J):
+                self._stage(1, j, x, r, pupdate, y)
+                works.append(self._a2a(self.bufB[j], self.bufA[j]))
+            for w in works:
+                if w is not None:
+                    w.wait()
+            self._stage(3, 0, x, r, 0, y)
+            works = [self._a2a(self.bufA[j], self.bufB[j]) for j in range(J)]
+            for j in range(J):
+                if works[j] is not None:
+                    works[j].wait()
+                self._stage(4, j, x, None, 0, y)
+            return y
+        self._stage(1, 0, x, r, pupdate, y)
+        self._stage(2, 0, x, r, 0, y)
         if self.layout.world > 1:
             exchange_fwd(self.spec, self.layout, self.group, out=self.specT)
             self.exchanged_bytes += self.spec.numel()*16*(self.layout.world-1)//self.layout.world
-        self._stage(3, x, y)
+        self._stage(3, 0, x, r, 0, y)
         if self.layout.world > 1:
             exchange_bwd(self.specT, self.layout, self.group, out=self.spec)
             self.exchanged_bytes += self.spec.numel()*16*(self.layout.world-1)//self.layout.world
-        self._stage(4, x, y)
-        self._stage(5, x, y)
+        self._stage(4, 0, x, r, 0, y)
+        self._stage(5, 0, x, r, 0, y)
         return y
 
     def last_dot(self):
@@ -151,29 +228,38 @@ class SlabGA(object):
         from . import ops
         return allreduce_sum(ops.dot(a, b), a.device, self.group)/self.pN
 
+    def _global_scalar(self, mode, want_norm):
+        """local partial sums -> device sum -> all-reduce -> rr / alpha / beta on the device"""
+        import torch.distributed as dist
+        L, lib, dev = self.L, self.dev.lib(), self.dev
+        L.check(lib.fh_cgd_local_sum(self.handle, dev.ptr(self.sums)))
+        if self.layout.world > 1:
+            dist.all_reduce(self.sums[:1], op=dist.ReduceOp.SUM, group=self.group)
+        norm = C.c_double()
+        L.check(lib.fh_cgd_scal(self.handle, dev.ptr(self.sums), mode, C.byref(norm) if want_norm else None))
+        return norm.value
+
     def cg(self, B, x0, tol=1e-6, maxiter=1000):
-        """general/solver.py:80-139; returns x (device, local slab), info."""
+        """general/solver.py:80-139 on the slab; alpha, beta, rr stay on the device, the host reads only
+        ||r|| (8 bytes) per iteration for the stop test.  Returns x (device, local slab), info."""
         from . import ops
         L, lib, dev = self.L, self.dev.lib(), self.dev
         n = self.D*self.nloc
+        shape = tuple(x0.shape)
         x = ops.clone(x0)
-        Ap = self.apply(x)
-        r = ops.axpby(1., B, -1., Ap)
-        p = ops.clone(r)
-        rr = self.dot(r, r)
-        kit = 0
-        norm_res = rr**0.5
+        vecs = dev.empty((3*n,))
+        r, p, Ap = (vecs[i*n:(i+1)*n].view(shape) for i in range(3))
+        self.apply(x, Ap)
+        L.check(lib.fh_cgd_init(self.handle, dev.ptr(B), dev.ptr(vecs)))
+        norm_res = self._global_scalar(0, True)
+        kit, have_beta = 0, 0
         hist = [norm_res]
         while norm_res > tol and kit < maxiter:
             kit += 1
-            self.apply(p, Ap)
-            alp = rr/self.last_dot()
-            loc = C.c_double()
-            L.check(lib.fh_cg_xr_update(n, dev.ptr(x), dev.ptr(r), dev.ptr(p), dev.ptr(Ap), float(alp), C.byref(loc)))
-            rrnext = allreduce_sum(loc.value, x.device, self.group)/self.pN
-            bet = rrnext/rr
-            rr = rrnext
-            L.check(lib.fh_cg_p_update(n, dev.ptr(p), dev.ptr(r), float(bet)))
-            norm_res = rr**0.5
+            self.apply(p, Ap, r=r, pupdate=have_beta)     # p = r + beta p folded into S1; <p,Ap> into S5
+            self._global_scalar(1, False)
+            L.check(lib.fh_cgd_update(self.handle, dev.ptr(x), dev.ptr(vecs)))
+            norm_res = self._global_scalar(2, True)
+            have_beta = 1
             hist.append(norm_res)
         return x, {'kit': kit, 'norm_res': norm_res if kit > 0 else 0, 'norm_res_log': np.array(hist)}

@@ -132,6 +132,23 @@ int64_t fh_ga_slab_work_doubles(const fh_plan* plan, int D, int n0_local, int n1
 int fh_ga_create_slab(fh_ga** op, const fh_plan* plan, int D, const double* A_local, int a_layout, const fh_green* g,
                       double* work, int n0_local, int n1_local, int n1_offset);
 int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch);
+/* Zero-copy, chunked slab pipeline (SURVEY §8e "overlap the all-to-all with the local FFT passes"):
+ * bufA / bufB are caller-owned exchange buffers of D*n0_local*N1*pitch complex128 each, organised as
+ * nchunk contiguous blocks [world][D][n0_local/nchunk][n1_local][pitch]; the axis-1 and axis-0 kernels
+ * address them directly, so each exchange is one all_to_all_single(bufB_j, bufA_j) (forward) or
+ * (bufA_j, bufB_j) (backward) per chunk with no pack/unpack pass.  N0, N1 in {16,...,2048} powers of two. */
+int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, void* bufB);
+/* one pipeline step with the CG fusions of fh_cg_steps (p = r + beta p in S1 when pupdate, <p,y> in S5):
+ * plain stages 1..5 without fh_ga_slab_direct; with it stage 1 = S1+S2 of `chunk` -> bufA,
+ * 3 = S3 on bufB, 4 = S4+S5 of `chunk` from bufA.  Replaces one Afun(P) of general/solver.py:125 */
+int fh_ga_slab_stage(fh_ga* op, int stage, int chunk, double* p, const double* r, int pupdate, double* y);
+/* CG of general/solver.py:113-136 split at its two global reductions: each piece leaves per-CTA partial
+ * sums, fh_cgd_local_sum folds them into sum_dev[0] (device), the caller all-reduces sum_dev over the
+ * ranks, fh_cgd_scal turns the global sum into rr/norm (mode 0), alpha (1) or beta/rr/norm (2). */
+int fh_cgd_init(fh_ga* op, const double* B, double* vecs);
+int fh_cgd_update(fh_ga* op, double* x, double* vecs);
+int fh_cgd_local_sum(fh_ga* op, double* sum_dev);
+int fh_cgd_scal(fh_ga* op, const double* sum_dev, int mode, double* norm_host);
 /* this rank's sum of x*y left on the device by the last fh_ga_stage(op, 5, x, y) */
 int fh_ga_last_dot(fh_ga* op, double* result_host);
 int fh_ga_destroy(fh_ga* op);

@@ -31,7 +31,7 @@ def main():
     from ffthompy_b200.slab import SlabGA, SlabLayout
     dev.init(local)
     ok = True
-    for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20)]):
+    for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20), (32, 16, 15), (128, 256, 32)]):
         if N[0] % world or N[1] % world:
             continue
         D = 6
@@ -41,24 +41,31 @@ def main():
         Afo = O.GA(Aval, Go[1]+Go[2], N)
         sl = slice(lay.n0_off, lay.n0_off+lay.n0l)
         _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3))
-        op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N)
         rng = np.random.default_rng(3)
         x = rng.standard_normal((D,)+N)
-        y = op.apply(dev.upload(x[:, sl]))
         ref = Afo(x)
-        err = np.abs(y.cpu().numpy()-ref[:, sl]).max()/np.abs(ref).max()
         E = np.zeros((D,)+N)
         E[0] = 1.
         B = Afo(-E)
         xo, io = O.cg(Afo, B, np.zeros_like(B), 1e-6, 1000, N)
-        xs, info = op.cg(dev.upload(B[:, sl]), dev.zeros((D, lay.n0l)+N[1:]), tol=1e-6, maxiter=1000)
-        errx = np.abs(xs.cpu().numpy()-xo[:, sl]).max()
-        good = err < 1e-12 and info['kit'] == io['kit'] and errx < 1e-9
-        ok = ok and good
-        if rank == 0:
-            print('N=%s world=%d: operator err %.2e, CG kit %d (oracle %d), solution err %.2e %s'
-                  % (N, world, err, info['kit'], io['kit'], errx, 'ok' if good else 'FAIL'), flush=True)
-        del op
+        for mode in ('packed', 'direct', 'direct1'):
+            op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N, direct=(False if mode == 'packed' else None),
+                        nchunk=(1 if mode == 'direct1' else None))
+            if mode != 'packed' and not op.direct:
+                if rank == 0:
+                    print('N=%s world=%d %s: exchange kernels do not cover this grid (packed path used)' % (N, world, mode))
+                continue
+            y = op.apply(dev.upload(x[:, sl]))
+            err = np.abs(y.cpu().numpy()-ref[:, sl]).max()/np.abs(ref).max()
+            xs, info = op.cg(dev.upload(B[:, sl]), dev.zeros((D, lay.n0l)+N[1:]), tol=1e-6, maxiter=1000)
+            errx = np.abs(xs.cpu().numpy()-xo[:, sl]).max()
+            good = err < 1e-12 and info['kit'] == io['kit'] and errx < 1e-9
+            ok = ok and good
+            if rank == 0:
+                print('N=%s world=%d %s(J=%d): operator err %.2e, CG kit %d (oracle %d), solution err %.2e %s'
+                      % (N, world, mode, op.nchunk, err, info['kit'], io['kit'], errx, 'ok' if good else 'FAIL'),
+                      flush=True)
+            del op
     if '--time' in sys.argv:
         n = int(sys.argv[sys.argv.index('--time')+1])
         N = (n, n, n)
@@ -72,7 +79,8 @@ def main():
         Ci = torch.from_numpy(O.elastic_mandel(10, 5)).to(dev.device())
         Ad = (Cm[:, :, None, None, None]*(1-phase)+Ci[:, :, None, None, None]*phase).contiguous()
         _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3))
-        op = SlabGA(Ad, G1h+G1s, N)
+        op = SlabGA(Ad, G1h+G1s, N, direct=(False if '--packed' in sys.argv else None),
+                    nchunk=(int(os.environ['SLAB_J']) if 'SLAB_J' in os.environ else None))
         E = dev.zeros((D, lay.n0l)+N[1:])
         E[0] = -1.
         B = op.apply(E)
@@ -92,6 +100,7 @@ def main():
         # K iterations + the initial residual = K+1 operator applications
         if rank == 0:
             per = t.item()/(K+1)
+            print('mode %s J=%d: ' % ('direct' if op.direct else 'packed', op.nchunk), end='')
             print('slab CG %d^3 on %d GPUs: %.3f ms per iteration-equivalent -> %.1f it/s, %.3e voxel-DOF/s; '
                   'NVLink: %.2f GB sent per GPU per operator application'
                   % (n, world, per*1e3, 1./per, D*n**3/per, op.exchanged_bytes/(K+1)/1e9), flush=True)

@@ -29,7 +29,7 @@ def _worker(rank, world, port, N, D, kind, q):
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, 'oracle'))
         import ffthom_oracle as O
-        from ffthompy_b200.slab import SlabLayout, exchange_fwd, exchange_bwd, allreduce_sum
+        from ffthompy_b200.slab import SlabLayout, exchange_fwd, exchange_bwd, allreduce_sum, direct_offsets
         dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
         lay = SlabLayout(N, world, rank)
         rng = np.random.default_rng(11)
@@ -67,6 +67,28 @@ def _worker(rank, world, port, N, D, kind, q):
         # round trip of the exchange and the scalar all-reduce
         rt = exchange_bwd(exchange_fwd(torch.from_numpy(specp), lay), lay).numpy()
         err_rt = np.abs(rt-specp).max()
+        # zero-copy chunk-major exchange blocks (fh_ga_slab_direct): scatter as S2 writes them, one
+        # all_to_all_single per chunk, gather as S3 reads them == the packed exchange; and back
+        for J in [j for j in (1, 2) if lay.n0l % j == 0]:
+            off1, off0, cs1, is1, cs0, ce = direct_offsets(lay, D, P, J)
+            n0c = lay.n0l//J
+            bufA = np.zeros(J*ce, dtype=complex)
+            cc, jj, ii, kk, tt = np.meshgrid(np.arange(D), np.arange(J), np.arange(n0c), np.arange(N[1]), np.arange(P),
+                                             indexing='ij')
+            idxA = jj*ce+cc*cs1+ii*is1+off1[kk]+tt
+            assert np.unique(idxA).size == idxA.size == bufA.size
+            bufA[idxA] = specp[cc, jj*n0c+ii, kk, tt]
+            tA, tB = torch.from_numpy(bufA).view(J, ce), torch.zeros(J, ce, dtype=torch.complex128)
+            for j in range(J):
+                dist.all_to_all_single(tB[j], tA[j])
+            c3, i3, k3, t3 = np.meshgrid(np.arange(D), np.arange(N[0]), np.arange(lay.n1l), np.arange(P), indexing='ij')
+            idxB = off0[i3]+c3*cs0+k3*P+t3
+            assert np.unique(idxB).size == idxB.size == bufA.size
+            assert np.array_equal(tB.numpy().reshape(-1)[idxB], specT)
+            tA.zero_()
+            for j in range(J):
+                dist.all_to_all_single(tA[j], tB[j])
+            assert np.array_equal(tA.numpy().reshape(-1)[idxA], specp[cc, jj*n0c+ii, kk, tt])
         tot = allreduce_sum(np.sum(x_loc*ref[:, sl]), torch.device('cpu'))
         err_dot = abs(tot-np.sum(x*ref))/abs(np.sum(x*ref))
         q.put((rank, float(err), float(err_rt), float(err_dot)))

@@ -19,3 +19,13 @@ def test_slab_cg_matches_oracle_on_two_gpus():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:]+out.stderr[-2000:]
     assert 'FAIL' not in out.stdout and out.stdout.count(' ok') >= 3
+
+
+def test_slab_pipeline_single_rank():
+    """the chunked zero-copy exchange pipeline and the device-scalar CG on one rank (the exchange is a
+    copy): every kernel of the multi-GPU path runs on a 1-GPU box"""
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '1',
+           '--master-addr', '127.0.0.1', '--master-port', '29543', os.path.join(ROOT, 'tests', 'slab_check.py')]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stdout[-2000:]+out.stderr[-2000:]
+    assert 'FAIL' not in out.stdout and out.stdout.count(' ok') >= 12
