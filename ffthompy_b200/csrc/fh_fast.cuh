@@ -19,6 +19,7 @@
 #pragma once
 #include "fh_fft.cuh"
 #include "fh_green.cuh"
+#include <cooperative_groups.h>
 
 template <int N>
 struct Fac2;
@@ -1464,5 +1465,222 @@ __global__ void __launch_bounds__(384) k_mid_green_map(cplx* __restrict__ data, 
     for (int e = threadIdx.x; e < TOT; e += NT) {
         const int t = e % T, row = (e / T) % N, cc = e / (T * N);
         data[rowoff[row] + (int64_t)cc * cstride + i0 + t] = buf[pidx(row) * L + cc * T + t];
+    }
+}
+
+
+// S3 on an exchange layout with cluster-cooperative global access.  A CTA can hold only T = 1..4 columns
+// of all D*N lines, i.e. 16..64-byte row segments — fine for HBM sectors, poor for NVLink packets when the
+// rows live in a peer's memory.  A thread-block cluster of CS CTAs therefore moves CS*T-column segments
+// (128 B and more): CTA q of the cluster loads every CS-th (component,row) pair at full segment width and
+// deals the columns out to their owners' shared memory over DSMEM; the store phase gathers the same way.
+// FFT / G^ / inverse FFT run on each CTA's own tile exactly as in k_mid_green_map.
+template <int N, int T, int CS, int KIND>
+__global__ void __launch_bounds__(384) k_mid_green_mapc(cplx* __restrict__ data, const cplx* __restrict__ tw,
+                                                         GreenDesc g, const int64_t* __restrict__ rowoff,
+                                                         int64_t cstride, int nh, int pitch) {
+    namespace cg = cooperative_groups;
+    constexpr int DIM = 3;
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int L = D * T, NT = 384, U = 4, TC = CS * T;
+    constexpr int PAIRS = D * N / CS;  // (component,row) pairs per CTA in the load / store phases
+    constexpr int TOT = PAIRS * TC;
+    static_assert((D * N) % CS == 0, "cluster size must divide D*N");
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][D*T]
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned q = cl.block_rank();
+    const int64_t ic = (int64_t)(blockIdx.x / CS) * TC;  // first column of the cluster's segment
+    const int64_t i0 = ic + (int64_t)q * T;              // first column of this CTA's tile
+    cplx* peer[CS];
+#pragma unroll
+    for (int u = 0; u < CS; ++u) peer[u] = cl.map_shared_rank(buf, u);
+    cl.sync();  // every CTA of the cluster is resident before its shared memory is written remotely
+    for (int e0 = threadIdx.x; e0 < TOT; e0 += U * NT) {
+        cplx c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                c[u] = data[rowoff[row] + (int64_t)cc * cstride + ic + col];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                peer[col / T][pidx(row) * L + cc * T + (col % T)] = c[u];
+            }
+        }
+    }
+    cl.sync();
+    smem_fft_inplace<N, false>(buf, L, tw);
+    for (int idx = threadIdx.x; idx < N * T; idx += NT) {
+        const int row = idx / T, tt = idx - row * T;
+        int k[3];
+        k[0] = fh_freq(smem_freq_of_row<N>(row), N);
+        const int64_t ii = i0 + tt;
+        const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+        k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
+        k[2] = fh_freq(i2, g.N[2]);
+        const bool valid = i2 < nh;
+        cplx* sr = buf + pidx(row) * L + tt;
+        cplx e[D];
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * T];
+        if (valid) {
+            green_apply<KIND, DIM>(g, k, e);
+        } else {
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int cc = 0; cc < D; ++cc) sr[cc * T] = e[cc];
+    }
+    __syncthreads();
+    smem_fft_inplace<N, true>(buf, L, tw);
+    cl.sync();
+    for (int e0 = threadIdx.x; e0 < TOT; e0 += U * NT) {
+        cplx c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                c[u] = peer[col / T][pidx(row) * L + cc * T + (col % T)];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e = e0 + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                data[rowoff[row] + (int64_t)cc * cstride + ic + col] = c[u];
+            }
+        }
+    }
+    cl.sync();  // no CTA may exit while a neighbour still reads its tile
+}
+
+
+// Persistent, software-pipelined form of k_mid_green_mapc: one cluster per CS SMs walks over the segments;
+// the (remote) loads of the NEXT segment are issued into registers before the transforms of the current
+// one and consumed after them, and the stores are fire-and-forget, so NVLink traffic in both directions
+// overlaps the FFT / G^ arithmetic instead of alternating with it (CTAs that all wait on the same link
+// fall into lock step otherwise).  D*N*T <= 6144 elements per CTA (16 complex numbers per thread in flight).
+template <int N, int T, int CS, int KIND>
+__global__ void __launch_bounds__(384, 1) k_mid_green_mapp(cplx* __restrict__ data, const cplx* __restrict__ tw,
+                                                            GreenDesc g, const int64_t* __restrict__ rowoff,
+                                                            int64_t cstride, int nh, int pitch, int64_t nseg) {
+    namespace cg = cooperative_groups;
+    constexpr int DIM = 3;
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int L = D * T, NT = 384, U = 4, TC = CS * T;
+    constexpr int PAIRS = D * N / CS;
+    constexpr int TOT = PAIRS * TC;
+    constexpr int UP = (TOT + NT - 1) / NT;
+    static_assert((D * N) % CS == 0 && UP <= 16, "segment does not fit the register pipeline");
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][D*T]
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned q = cl.block_rank();
+    const int64_t ncl = gridDim.x / CS;
+    cplx* peer[CS];
+#pragma unroll
+    for (int u = 0; u < CS; ++u) peer[u] = cl.map_shared_rank(buf, u);
+    cplx pre[UP];
+    int64_t seg = blockIdx.x / CS;
+    if (seg < nseg) {
+        const int64_t ic = seg * TC;
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+            const int e = threadIdx.x + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                pre[u] = data[rowoff[row] + (int64_t)cc * cstride + ic + col];
+            }
+        }
+    }
+    cl.sync();
+    for (; seg < nseg; seg += ncl) {
+        const int64_t ic = seg * TC;
+        const int64_t i0 = ic + (int64_t)q * T;
+#pragma unroll
+        for (int u = 0; u < UP; ++u) {
+            const int e = threadIdx.x + u * NT;
+            if (e < TOT) {
+                const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                const int cc = pi / N, row = pi - cc * N;
+                peer[col / T][pidx(row) * L + cc * T + (col % T)] = pre[u];
+            }
+        }
+        cl.sync();
+        if (seg + ncl < nseg) {  // next segment: in flight during the transforms
+            const int64_t icn = (seg + ncl) * TC;
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                const int e = threadIdx.x + u * NT;
+                if (e < TOT) {
+                    const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                    const int cc = pi / N, row = pi - cc * N;
+                    pre[u] = data[rowoff[row] + (int64_t)cc * cstride + icn + col];
+                }
+            }
+        }
+        smem_fft_inplace<N, false>(buf, L, tw);
+        for (int idx = threadIdx.x; idx < N * T; idx += NT) {
+            const int row = idx / T, tt = idx - row * T;
+            int k[3];
+            k[0] = fh_freq(smem_freq_of_row<N>(row), N);
+            const int64_t ii = i0 + tt;
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
+            k[2] = fh_freq(i2, g.N[2]);
+            const bool valid = i2 < nh;
+            cplx* sr = buf + pidx(row) * L + tt;
+            cplx e[D];
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) e[cc] = sr[cc * T];
+            if (valid) {
+                green_apply<KIND, DIM>(g, k, e);
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < D; ++cc) e[cc] = make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int cc = 0; cc < D; ++cc) sr[cc * T] = e[cc];
+        }
+        __syncthreads();
+        smem_fft_inplace<N, true>(buf, L, tw);
+        cl.sync();
+        for (int e0 = threadIdx.x; e0 < TOT; e0 += U * NT) {
+            cplx c[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * NT;
+                if (e < TOT) {
+                    const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                    const int cc = pi / N, row = pi - cc * N;
+                    c[u] = peer[col / T][pidx(row) * L + cc * T + (col % T)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int e = e0 + u * NT;
+                if (e < TOT) {
+                    const int col = e % TC, pi = (e / TC) * CS + (int)q;
+                    const int cc = pi / N, row = pi - cc * N;
+                    data[rowoff[row] + (int64_t)cc * cstride + ic + col] = c[u];
+                }
+            }
+        }
+        cl.sync();  // tiles are free for the next deal (and nobody exits while a neighbour reads its tile)
     }
 }

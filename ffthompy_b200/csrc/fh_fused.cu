@@ -69,6 +69,8 @@ struct fh_ga {
     cplx* sd_bufB;      // S3 in place (receive buffer forward, send buffer backward)
     int64_t* sd_off1;   // [N1] row offsets of the axis-1 passes inside one chunk of bufA
     int64_t* sd_off0;   // [N0] row offsets of the axis-0 pass inside bufB
+    int64_t sd_cs0;     // component stride of the axis-0 pass
+    int sd_peer;        // 1: the axis-0 pass reads/writes the peers' x-slab spectra directly (fh_ga_slab_peer)
 };
 
 // rows handled by the next S1 / S5 launch: element offsets into fields (ro) and spectrum rows (so),
@@ -1264,6 +1266,62 @@ static int launch_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, cons
     }
     return fh_set_error(FH_ERR_UNSUPPORTED, "no slab-exchange kernel for N1=%d", N);
 }
+template <int N, int T, int CS, int KIND>
+static int launch_mid_mapc(fh_ga* op, size_t smem) {
+    const fh_plan* p = op->plan;
+    const int64_t inner = (int64_t)op->n1l * op->pitch;
+    int rc;
+    if ((rc = smem_attr(k_mid_green_mapc<N, T, CS, KIND>, smem))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(inner / T), 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = fh_stream();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    FH_CUDA(cudaLaunchKernelEx(&cfg, k_mid_green_mapc<N, T, CS, KIND>, op->sd_peer ? op->spec : op->sd_bufB,
+                               (const cplx*)p->ax[0].tw, op->g, (const int64_t*)op->sd_off0, op->sd_cs0, p->nh,
+                               op->pitch));
+    fh_count_launch();
+    return FH_OK;
+}
+template <int N, int T, int CS, int KIND>
+static int launch_mid_mapp(fh_ga* op, size_t smem) {
+    const fh_plan* p = op->plan;
+    const int64_t inner = (int64_t)op->n1l * op->pitch;
+    const int64_t nseg = inner / (T * CS);
+    int rc;
+    if ((rc = smem_attr(k_mid_green_mapp<N, T, CS, KIND>, smem))) return rc;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CS * fh_num_sms()), 1, 1);
+    cfg.blockDim = dim3(384, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = fh_stream();
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    static int ncl_cache[9] = {0};  // co-resident clusters of this size (same smem footprint for every N of a T class)
+    int ncl = 0;
+    FH_CUDA(cudaOccupancyMaxActiveClusters(&ncl, k_mid_green_mapp<N, T, CS, KIND>, &cfg));
+    (void)ncl_cache;
+    if (ncl < 1) return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: no cluster of %d CTAs fits", CS);
+    if ((int64_t)ncl > nseg) ncl = (int)nseg;
+    cfg.gridDim = dim3((unsigned)(CS * ncl), 1, 1);
+    FH_CUDA(cudaLaunchKernelEx(&cfg, k_mid_green_mapp<N, T, CS, KIND>, op->sd_peer ? op->spec : op->sd_bufB,
+                               (const cplx*)p->ax[0].tw, op->g, (const int64_t*)op->sd_off0, op->sd_cs0, p->nh,
+                               op->pitch, nseg));
+    fh_count_launch();
+    return FH_OK;
+}
 template <int N, int T, int KIND>
 static int launch_mid_map_NT(fh_ga* op) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? 3 : 6;
@@ -1272,10 +1330,28 @@ static int launch_mid_map_NT(fh_ga* op) {
     const size_t smem = (size_t)(N + N / 16) * D * T * sizeof(cplx);
     if (smem > (size_t)fh_max_smem_optin())
         return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: N0=%d D=%d does not fit shared memory", N, D);
+    // rows in peer memory: move 128-byte (FH_XSEG=256: 256-byte) segments through a CTA cluster
+    if (op->sd_peer && op->sd_world > 1) {
+        static const int seg = env_int("FH_XSEG", 128);
+        const int64_t ntile = inner / T;
+        static const int xpipe = env_int("FH_XPIPE", 1);
+        if constexpr (D * N * T <= 6144 && (T == 2 || T == 4)) {
+            if (xpipe && ntile % (8 / T) == 0) return launch_mid_mapp<N, T, 8 / T, KIND>(op, smem);
+        }
+        if constexpr (T == 4) {
+            if (seg >= 256 && ntile % 4 == 0) return launch_mid_mapc<N, T, 4, KIND>(op, smem);
+            if (seg >= 128 && ntile % 2 == 0) return launch_mid_mapc<N, T, 2, KIND>(op, smem);
+        } else if constexpr (T == 2) {
+            if (seg >= 256 && ntile % 8 == 0) return launch_mid_mapc<N, T, 8, KIND>(op, smem);
+            if (seg >= 128 && ntile % 4 == 0) return launch_mid_mapc<N, T, 4, KIND>(op, smem);
+        } else {
+            if (seg >= 128 && ntile % 8 == 0) return launch_mid_mapc<N, T, 8, KIND>(op, smem);
+        }
+    }
     int rc;
     if ((rc = smem_attr(k_mid_green_map<N, T, KIND, 3>, smem))) return rc;
     k_mid_green_map<N, T, KIND, 3><<<(unsigned)(inner / T), 384, smem, fh_stream()>>>(
-        op->sd_bufB, p->ax[0].tw, op->g, op->sd_off0, (int64_t)op->sd_n0c * inner, p->nh, op->pitch);
+        op->sd_peer ? op->spec : op->sd_bufB, p->ax[0].tw, op->g, op->sd_off0, op->sd_cs0, p->nh, op->pitch);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -1341,12 +1417,59 @@ extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, v
     op->sd_world = world;
     op->sd_nchunk = nchunk;
     op->sd_n0c = n0c;
+    op->sd_cs0 = (int64_t)n0c * inner;
+    op->sd_peer = 0;
     op->sd_bufA = (cplx*)bufA;
     op->sd_bufB = (cplx*)bufB;
     // padding columns travel with the rows: keep them zero
     const size_t bytes = sizeof(cplx) * (size_t)D * n0l * p->N[1] * P;
     FH_CUDA(cudaMemsetAsync(bufA, 0, bytes, fh_stream()));
     FH_CUDA(cudaMemsetAsync(bufB, 0, bytes, fh_stream()));
+    return FH_OK;
+}
+
+// Fused axis-0 pass + exchange over peer memory: every rank keeps its x-slab half spectrum
+// [D][n0l][N1][pitch] in memory its peers can address (NVLink peer mappings, e.g. torch symmetric memory);
+// S3 of rank q gathers row i0 of its k1 range straight from the owner of plane i0 (remote loads),
+// applies G^ and scatters the result back to the same place (remote stores).  No exchange buffer, no
+// all-to-all: the transfer rides inside the kernel's own load/store phases.  The caller puts a device
+// barrier across the ranks before and after stage 3.  peer_spec[g] = rank g's spectrum base (fh_ga_buffers)
+// as mapped into THIS process.
+extern "C" int fh_ga_slab_peer(fh_ga* op, int world, int rank, const void* const* peer_spec) {
+    FH_REQUIRE(op && peer_spec && world >= 1 && rank >= 0 && rank < world, "fh_ga_slab_peer: bad argument");
+    const fh_plan* p = op->plan;
+    FH_REQUIRE(p->dim == 3, "fh_ga_slab_peer: a 3-D slab operator is required");
+    FH_REQUIRE((int64_t)op->n0l * world == p->N[0] && (int64_t)op->n1l * world == p->N[1],
+               "fh_ga_slab_peer: slab extents do not match world=%d", world);
+    FH_REQUIRE(op->g.ioff1 == rank * op->n1l, "fh_ga_slab_peer: rank %d does not own the k1 range of this operator", rank);
+    FH_REQUIRE(peer_spec[rank] == (const void*)op->spec, "fh_ga_slab_peer: peer_spec[rank] must be this operator's spectrum");
+    if (!fh_map_len(p->N[0]))
+        return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_peer: N0=%d not in the exchange kernel family", p->N[0]);
+    const int P = op->pitch, n0l = op->n0l, N1 = p->N[1];
+    int64_t* h0 = (int64_t*)malloc(sizeof(int64_t) * p->N[0]);
+    if (!h0) return fh_set_error(FH_ERR_ALLOC, "fh_ga_slab_peer: out of host memory");
+    for (int i0 = 0; i0 < p->N[0]; ++i0) {
+        const int g = i0 / n0l, i0l = i0 % n0l;
+        const intptr_t delta = (intptr_t)peer_spec[g] - (intptr_t)op->spec;
+        if (!peer_spec[g] || delta % (intptr_t)sizeof(cplx)) {
+            free(h0);
+            return fh_set_error(FH_ERR_ARG, "fh_ga_slab_peer: peer %d spectrum pointer is null or misaligned", g);
+        }
+        h0[i0] = (int64_t)(delta / (intptr_t)sizeof(cplx)) + ((int64_t)i0l * N1 + (int64_t)rank * op->n1l) * P;
+    }
+    if (op->sd_off1) cudaFree(op->sd_off1);
+    op->sd_off1 = op->sd_off0 = NULL;
+    cudaError_t e = cudaMalloc((void**)&op->sd_off1, sizeof(int64_t) * p->N[0]);
+    if (e == cudaSuccess) e = cudaMemcpy(op->sd_off1, h0, sizeof(int64_t) * p->N[0], cudaMemcpyHostToDevice);
+    free(h0);
+    if (e != cudaSuccess) return fh_set_error(FH_ERR_CUDA, "fh_ga_slab_peer: %s", cudaGetErrorString(e));
+    op->sd_off0 = op->sd_off1;
+    op->sd_cs0 = (int64_t)n0l * N1 * P;
+    op->sd_world = world;
+    op->sd_nchunk = 1;
+    op->sd_n0c = n0l;
+    op->sd_peer = 1;
+    op->sd_bufA = op->sd_bufB = NULL;
     return FH_OK;
 }
 
@@ -1358,7 +1481,9 @@ extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, v
 extern "C" int fh_ga_slab_stage(fh_ga* op, int stage, int chunk, double* p, const double* r, int pupdate, double* y) {
     FH_REQUIRE(op && p && y, "fh_ga_slab_stage: null argument");
     int np = 0, rc;
-    if (!op->sd_world) {
+    if (!op->sd_world || op->sd_peer) {
+        if (op->sd_peer && stage == 3)
+            return (op->g.kind == FH_GREEN_SCALAR) ? launch_mid_map<FH_GREEN_SCALAR>(op) : launch_mid_map<FH_GREEN_ELASTIC>(op);
         rc = ga_stage(op, stage, p, r, pupdate, y, 1, &np);
         if (stage == 5 && !rc) op->last_npart = np;
         return rc;

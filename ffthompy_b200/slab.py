@@ -10,8 +10,13 @@ operator application is
     S4, S5  local
 and CG reduces its two scalars per iteration with all-reduce (device tensors, no host round trip).
 
-Two exchange modes:
-* direct (default when N0, N1 are powers of two 16..2048): the exchange buffers are chunk-major blocks
+Three exchange modes:
+* peer (default on NVLink-connected GPUs when N0 is a power of two 16..2048): the x-slab spectra live in
+  torch symmetric memory (peer-mapped over NVLink); S3 of each rank gathers its rows straight from the
+  owners' spectra with remote loads, applies G^ and scatters the result back with remote stores
+  (fh_ga_slab_peer).  The exchange is fused into the axis-0 kernel — no all-to-all, no exchange buffer,
+  two device barriers per operator application.
+* direct (N0, N1 powers of two 16..2048): the exchange buffers are chunk-major blocks
   [J][G][D][n0l/J][n1l][pitch] that the axis-1 / axis-0 kernels address in place (fh_ga_slab_direct), so
   an exchange is ONE all_to_all_single per chunk with no pack/unpack pass, issued asynchronously:
   chunk j travels over NVLink while S1+S2 of chunk j+1 (forward) or S4+S5 of chunk j-1 (backward) run.
@@ -105,10 +110,10 @@ def direct_offsets(layout, D, P, nchunk):
 class SlabGA(object):
     """y = F^-1 G^ F (A x) on slab-decomposed fields, and the CG loop of general/solver.py:80-139
     over it.  `A_local`: device tensor [D][D][n0l][N1][N2]; `G`: lazy GreenTensor on the GLOBAL grid.
-    `direct`: None = zero-copy chunked exchange when the kernels support the grid, True = require it,
-    False = packed exchange; `nchunk`: x-plane chunks per exchange (default: up to 4)."""
+    `exchange`: None = best available ('peer', else 'direct', else 'packed'), or one of those names to
+    require it; `nchunk`: x-plane chunks per exchange in direct mode (default: up to 4)."""
 
-    def __init__(self, A_local, G, N, group=None, direct=None, nchunk=None):
+    def __init__(self, A_local, G, N, group=None, exchange=None, nchunk=None):
         import torch
         import torch.distributed as dist
         from . import _lib as L
@@ -119,11 +124,25 @@ class SlabGA(object):
         self.D = D = int(A_local.shape[0])
         assert tuple(A_local.shape) == (D, D, lay.n0l, lay.N[1], lay.N[2])
         assert G.lazy and G.fft_form == 'r' and tuple(int(n) for n in G.N) == lay.N
+        assert exchange in (None, 'peer', 'p2p', 'direct', 'packed')
         self.A = A_local.contiguous()
         self.plan = dev.plan(lay.N)
         lib = dev.lib()
         nwork = int(lib.fh_ga_slab_work_doubles(self.plan, D, lay.n0l, lay.n1l))
-        self.work = dev.zeros((nwork,))
+        # peer mode: the workspace (with the spectrum inside) is symmetric memory, mapped by every rank
+        self.symm = None
+        if exchange in (None, 'peer') and world > 1:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                self.work = symm_mem.empty(nwork, dtype=torch.float64, device=dev.device())
+                self.work.zero_()
+                self.symm = symm_mem.rendezvous(self.work, group if group is not None else dist.group.WORLD)
+            except Exception:
+                if exchange == 'peer':
+                    raise
+                self.symm = None
+        if self.symm is None:
+            self.work = dev.zeros((nwork,))
         self.handle = C.c_void_p()
         g = G.descriptor()
         L.check(lib.fh_ga_create_slab(C.byref(self.handle), self.plan, D, dev.ptr(self.A), 0, C.byref(g),
@@ -142,24 +161,65 @@ class SlabGA(object):
         self.pN = float(np.prod(lay.N))
         self.exchanged_bytes = 0
         self.sums = dev.zeros((2,))
-        # exchange mode
-        self.direct, self.nchunk = False, 1
-        if direct is not False:
+        self.mode, self.nchunk = 'packed', 1
+        if exchange in (None, 'peer') and (self.symm is not None or world == 1):
+            if self.symm is not None:
+                ptrs = [int(b)+(spec.value-base) for b in self.symm.buffer_ptrs]
+                assert ptrs[rank] == spec.value
+            else:
+                ptrs = [spec.value]
+            arr = (C.c_void_p*world)(*ptrs)
+            rc = lib.fh_ga_slab_peer(self.handle, world, rank, arr)
+            if rc == 0:
+                self.mode = 'peer'
+            elif exchange == 'peer':
+                L.check(rc)
+        if self.mode == 'packed' and exchange in (None, 'direct', 'p2p'):
             cands = [int(nchunk)] if nchunk else [j for j in (4, 2, 1) if lay.n0l % j == 0]
             nel = D*lay.n0l*lay.N[1]*P
-            bufA = torch.zeros(nel, dtype=torch.complex128, device=dev.device())
-            # the y-slab workspace doubles as exchange buffer B (on one rank it aliases the x-slab spectrum)
-            bufB = self.specT.reshape(-1) if world > 1 else torch.zeros_like(bufA)
+            self.xsymm = None
+            if exchange == 'p2p' and world > 1:
+                # both exchange buffers in symmetric memory: chunks are PUSHED into the peers' buffers by the
+                # copy engines (cudaMemcpyAsync over NVLink on a side stream) while the SMs transform the
+                # next chunk; no NCCL kernel competes for SMs and nothing is staged
+                import torch.distributed._symmetric_memory as symm_mem
+                xb = symm_mem.empty(4*nel, dtype=torch.float64, device=dev.device())
+                xb.zero_()
+                self.xsymm = symm_mem.rendezvous(xb, group if group is not None else dist.group.WORLD)
+                cview = lambda t: torch.view_as_complex(t.reshape(-1, 2))
+                bufA, bufB = cview(xb[:2*nel]), cview(xb[2*nel:])
+                self._xb = xb
+            else:
+                bufA = torch.zeros(nel, dtype=torch.complex128, device=dev.device())
+                # the y-slab workspace doubles as exchange buffer B (on one rank it aliases the x-slab spectrum)
+                bufB = self.specT.reshape(-1) if world > 1 else torch.zeros_like(bufA)
+            rc = -1
             for J in cands:
                 rc = lib.fh_ga_slab_direct(self.handle, world, J, dev.ptr(bufA), dev.ptr(bufB))
                 if rc == 0:
-                    self.direct, self.nchunk = True, J
+                    self.mode, self.nchunk = 'direct', J
                     self.bufA, self.bufB = bufA.view(J, -1), bufB.view(J, -1)
                     break
-            if not self.direct:
-                del bufA
-                if direct is True:
+            if self.mode != 'direct':
+                del bufA, bufB
+                if exchange in ('direct', 'p2p'):
                     L.check(rc)
+            elif self.xsymm is not None:
+                self.mode = 'p2p'
+                J = self.nchunk
+                self.blkA, self.blkB = self.bufA.view(J, world, -1), self.bufB.view(J, world, -1)
+                self.peerA, self.peerB = [], []
+                for g_ in range(world):
+                    pb = self.xsymm.get_buffer(g_, (4*nel,), torch.float64, 0)
+                    self.peerA.append(cview(pb[:2*nel]).view(J, world, -1))
+                    self.peerB.append(cview(pb[2*nel:]).view(J, world, -1))
+                self.cstream = torch.cuda.Stream()
+        self.direct = self.mode in ('direct', 'p2p')
+
+    def _barrier(self):
+        """device-side barrier across the ranks on the current stream (symmetric-memory signal pads)"""
+        if self.symm is not None:
+            self.symm.barrier()
 
     def __del__(self):
         try:
@@ -187,6 +247,19 @@ class SlabGA(object):
         update x <- r + beta*x (beta on the device) is folded into S1, as in fh_cg_steps."""
         if y is None:
             y = self.dev.empty(x.shape)
+        if self.mode == 'peer':
+            self._stage(1, 0, x, r, pupdate, y)
+            self._stage(2, 0, x, r, 0, y)
+            self._barrier()                      # every rank's S2 output is in place
+            self._stage(3, 0, x, r, 0, y)        # remote loads -> G^ -> remote stores
+            self._barrier()                      # every rank's rows are back
+            self._stage(4, 0, x, r, 0, y)
+            self._stage(5, 0, x, r, 0, y)
+            lay = self.layout
+            self.exchanged_bytes += 2*self.spec.numel()*16*(lay.world-1)//lay.world
+            return y
+        if self.mode == 'p2p':
+            return self._apply_p2p(x, y, r, pupdate)
         if self.direct:
             J = self.nchunk
             works = []
@@ -214,6 +287,45 @@ class SlabGA(object):
             self.exchanged_bytes += self.spec.numel()*16*(self.layout.world-1)//self.layout.world
         self._stage(4, 0, x, r, 0, y)
         self._stage(5, 0, x, r, 0, y)
+        return y
+
+    def _apply_p2p(self, x, y, r, pupdate):
+        """chunk-pipelined exchange by copy-engine pushes into the peers' symmetric buffers:
+        forward  S1+S2(chunk j+1) on the SMs  ||  chunk j -> peers' buffer B over NVLink
+        backward chunk j+1 -> peers' buffer A  ||  S4+S5(chunk j) on the SMs"""
+        import torch
+        J, G, me = self.nchunk, self.layout.world, self.layout.rank
+        main, cs = torch.cuda.current_stream(), self.cstream
+        order = [(me+k) % G for k in range(G)]            # start with the local block, then ring order
+        for j in range(J):
+            self._stage(1, j, x, r, pupdate, y)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                for g in order:
+                    self.peerB[g][j, me].copy_(self.blkA[j, g], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        main.wait_event(ev)
+        self.xsymm.barrier(channel=0)                     # every rank's pushes have landed
+        self._stage(3, 0, x, r, 0, y)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        cs.wait_event(ev)
+        evs = []
+        with torch.cuda.stream(cs):
+            for j in range(J):
+                for g in order:
+                    self.peerA[g][j, me].copy_(self.blkB[j, g], non_blocking=True)
+                self.xsymm.barrier(channel=1)             # chunk j of every rank is in place
+                e = torch.cuda.Event()
+                e.record(cs)
+                evs.append(e)
+        for j in range(J):
+            main.wait_event(evs[j])
+            self._stage(4, j, x, None, 0, y)
+        self.exchanged_bytes += 2*self.bufA.numel()*16*(G-1)//G
         return y
 
     def last_dot(self):

@@ -138,6 +138,12 @@ int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch);
  * address them directly, so each exchange is one all_to_all_single(bufB_j, bufA_j) (forward) or
  * (bufA_j, bufB_j) (backward) per chunk with no pack/unpack pass.  N0, N1 in {16,...,2048} powers of two. */
 int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, void* bufB);
+/* Fused axis-0 pass + exchange over NVLink peer memory (no all-to-all, no exchange buffer): stage 3 of
+ * rank `rank` loads row i0 of its k1 range from the x-slab spectrum of the rank that owns plane i0
+ * (peer_spec[g] = rank g's fh_ga_buffers spectrum as mapped into this process, e.g. torch symmetric
+ * memory), applies G^ and stores the result back in place.  The caller issues a device barrier across
+ * the ranks before and after stage 3 of fh_ga_slab_stage.  N0 in {16,...,2048} powers of two. */
+int fh_ga_slab_peer(fh_ga* op, int world, int rank, const void* const* peer_spec);
 /* one pipeline step with the CG fusions of fh_cg_steps (p = r + beta p in S1 when pupdate, <p,y> in S5):
  * plain stages 1..5 without fh_ga_slab_direct; with it stage 1 = S1+S2 of `chunk` -> bufA,
  * 3 = S3 on bufB, 4 = S4+S5 of `chunk` from bufA.  Replaces one Afun(P) of general/solver.py:125 */

@@ -32,7 +32,7 @@ def main():
     dev.init(local)
     ok = True
     for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20), (32, 16, 15), (128, 256, 32)]):
-        if N[0] % world or N[1] % world:
+        if N[0] % world or N[1] % world or (world > 2 and np.prod(N) > 300000):
             continue
         D = 6
         lay = SlabLayout(N, world, rank)
@@ -48,12 +48,15 @@ def main():
         E[0] = 1.
         B = Afo(-E)
         xo, io = O.cg(Afo, B, np.zeros_like(B), 1e-6, 1000, N)
-        for mode in ('packed', 'direct', 'direct1'):
-            op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N, direct=(False if mode == 'packed' else None),
-                        nchunk=(1 if mode == 'direct1' else None))
-            if mode != 'packed' and not op.direct:
+        for mode in ('packed', 'direct', 'direct1', 'peer') + (('p2p',) if world > 1 else ()):
+            try:
+                op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N, exchange=mode.rstrip('1'),
+                            nchunk=(1 if mode == 'direct1' else None))
+            except Exception as e:
+                if 'not in the' not in str(e) and 'cannot run' not in str(e):
+                    raise
                 if rank == 0:
-                    print('N=%s world=%d %s: exchange kernels do not cover this grid (packed path used)' % (N, world, mode))
+                    print('N=%s world=%d %s: exchange kernels do not cover this grid' % (N, world, mode))
                 continue
             y = op.apply(dev.upload(x[:, sl]))
             err = np.abs(y.cpu().numpy()-ref[:, sl]).max()/np.abs(ref).max()
@@ -66,44 +69,109 @@ def main():
                       % (N, world, mode, op.nchunk, err, info['kit'], io['kit'], errx, 'ok' if good else 'FAIL'),
                       flush=True)
             del op
-    if '--time' in sys.argv:
-        n = int(sys.argv[sys.argv.index('--time')+1])
+    def time_case(n, kind, mode):
+        """CG iterations of the BASELINE generator (Bernoulli(0.3) two-phase medium, seed 20240901) at n^3;
+        every rank draws only its own slab (PCG64.advance: bit-identical to the one-shot array)"""
         N = (n, n, n)
-        D = 6
+        D = 6 if kind == 'elastic' else 3
         lay = SlabLayout(N, world, rank)
-        rng = np.random.default_rng(20240901)
-        full = rng.random(N) < 0.3   # same global microstructure on every rank, each keeps its slab
-        phase = torch.from_numpy(full[lay.n0_off:lay.n0_off+lay.n0l]).to(dev.device()).to(torch.float64)
+        bg = np.random.PCG64(20240901)
+        bg.advance(lay.n0_off*N[1]*N[2])
+        full = np.random.Generator(bg).random((lay.n0l, N[1], N[2])) < 0.3
+        phase = torch.from_numpy(full).to(dev.device()).to(torch.float64)
         del full
-        Cm = torch.from_numpy(O.elastic_mandel(1, 1)).to(dev.device())
-        Ci = torch.from_numpy(O.elastic_mandel(10, 5)).to(dev.device())
+        if kind == 'elastic':
+            Cm = torch.from_numpy(O.elastic_mandel(1, 1)).to(dev.device())
+            Ci = torch.from_numpy(O.elastic_mandel(10, 5)).to(dev.device())
+            _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3))
+            G = G1h+G1s
+        else:
+            Cm = torch.eye(3, dtype=torch.float64, device=dev.device())
+            Ci = 11.*torch.eye(3, dtype=torch.float64, device=dev.device())
+            G = proj.scalar(np.array(N), np.ones(3))[1]
         Ad = (Cm[:, :, None, None, None]*(1-phase)+Ci[:, :, None, None, None]*phase).contiguous()
-        _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3))
-        op = SlabGA(Ad, G1h+G1s, N, direct=(False if '--packed' in sys.argv else None),
+        del phase
+        op = SlabGA(Ad, G, N, exchange=mode or None,
                     nchunk=(int(os.environ['SLAB_J']) if 'SLAB_J' in os.environ else None))
         E = dev.zeros((D, lay.n0l)+N[1:])
         E[0] = -1.
         B = op.apply(E)
+        del E
         x0 = dev.zeros((D, lay.n0l)+N[1:])
         op.cg(B, x0, tol=0., maxiter=3)
         op.exchanged_bytes = 0
-        dist.barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
         K = 20
-        xs, info = op.cg(B, x0, tol=0., maxiter=K)
         torch.cuda.synchronize()
         dist.barrier()
-        dt = time.perf_counter()-t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev.device())
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # K iterations + the initial residual = K+1 operator applications
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        xs, info = op.cg(B, x0, tol=0., maxiter=K)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)*1e-3], dtype=torch.float64, device=dev.device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)       # device time, max over ranks
         if rank == 0:
+            # K iterations + the initial residual = K+1 operator applications
             per = t.item()/(K+1)
-            print('mode %s J=%d: ' % ('direct' if op.direct else 'packed', op.nchunk), end='')
-            print('slab CG %d^3 on %d GPUs: %.3f ms per iteration-equivalent -> %.1f it/s, %.3e voxel-DOF/s; '
-                  'NVLink: %.2f GB sent per GPU per operator application'
-                  % (n, world, per*1e3, 1./per, D*n**3/per, op.exchanged_bytes/(K+1)/1e9), flush=True)
+            nvox = float(n)**3
+            b_iter = (15*8*D+8*D*(D+1)//2)*nvox           # SURVEY 8(d): 15F + C_A(sym)
+            nv = op.exchanged_bytes/(K+1)
+            rec = {'workload': '%s %d^3' % (kind, n), 'n_gpus': world, 'exchange': op.mode, 'chunks': op.nchunk,
+                   'ms_per_iteration': round(per*1e3, 3), 'it_per_s': round(1./per, 2),
+                   'voxel_dof_per_s': D*nvox/per, 'hbm_roofline_frac': b_iter/per/(world*6556.8e9),
+                   'nvlink_GB_sent_per_gpu_per_iteration': round(nv/1e9, 3),
+                   'nvlink_frac_of_900GBps': nv/per/900e9}
+            import json
+            print('SLAB ' + json.dumps(rec), flush=True)
+            print('mode %s J=%d: slab CG %s %d^3 on %d GPUs: %.3f ms per iteration-equivalent -> %.1f it/s, '
+                  '%.3e voxel-DOF/s, %.1f%% of the aggregate HBM roofline; NVLink %.2f GB sent per GPU per iteration'
+                  % (op.mode, op.nchunk, kind, n, world, per*1e3, 1./per, D*nvox/per,
+                     100*rec['hbm_roofline_frac'], nv/1e9), flush=True)
+        if '--stages' in sys.argv and op.mode in ('peer', 'packed'):
+            # per-stage device time with every rank inside the same stage (barrier in front of each launch)
+            x = dev.zeros((D, lay.n0l)+N[1:])
+            x.normal_()
+            y = dev.zeros((D, lay.n0l)+N[1:])
+            out = []
+            for st in (1, 2, 3, 4, 5):
+                ts = []
+                for rep in range(4):
+                    dist.barrier()
+                    op._barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    op._stage(st, 0, x, None, 0, y)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    ts.append(e0.elapsed_time(e1))
+                out.append('S%d %.3f' % (st, min(ts[1:])))
+            ts = []
+            for rep in range(4):
+                dist.barrier()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                op.apply(x, y)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            out.append('apply %.3f' % min(ts[1:]))
+            if rank == 0:
+                print('stages [ms] (%s): ' % op.mode+' | '.join(out), flush=True)
+        del op, Ad, B, x0, xs
+        torch.cuda.empty_cache()
+
+    modes = (os.environ.get('SLAB_X') or '').split(',')
+    for flag, kind in (('--time', 'elastic'), ('--time-scalar', 'scalar')):
+        if flag in sys.argv:
+            n = int(sys.argv[sys.argv.index(flag)+1])
+            for mode in modes:
+                try:
+                    time_case(n, kind, mode)
+                except Exception as e:   # e.g. an exchange mode that does not cover this grid
+                    if rank == 0:
+                        print('mode %s %s %d^3: %s' % (mode, kind, n, str(e)[:200]), flush=True)
+                    torch.cuda.empty_cache()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
