@@ -7,8 +7,9 @@ voxel-DOF/s at 256^3 elasticity; % of the HBM roofline).
 A "step" is ONE CG iteration of the hot path (operator application G·A·p, two dot products, three
 vector updates) on the BASELINE config-3 workload: 3-D linear elasticity (D = 6, Mandel), random
 two-phase microstructure (seed 20240901, 30 % inclusions, K/G = 1/1 | 10/5), GaNi, n^3 grid.
-N > 1 GPUs run N independent replicas of that workload (the unit loads / microstructure samples of
-a homogenisation campaign are independent solves: weak scaling, no data-path collective).
+N > 1 GPUs (torchrun, one rank per GPU) run ONE slab-decomposed solve of BASELINE config 4 — the same
+generator at 512^3, x-planes split over the ranks, FFT transposes over NVLink (ffthompy_b200/slab.py),
+CG scalars by all-reduce; `--mode replicas` runs N independent 256^3 solves instead.
 
 `--impl reference` times the CPU restatement of the reference's NumPy path (oracle/, the reference
 itself cannot travel to the GPU box) on a bounded sample of the same workload.
@@ -151,7 +152,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n, ngpu, where):
+def workload_config(n, ngpu, where, slab=None):
+    if slab is not None:
+        return {'workload': '3-D linear elasticity (D=6 Mandel), random two-phase microstructure seed %d, 30%% '
+                            'inclusions, GaNi %d^3, Galerkin CG, slab-decomposed over %d GPUs (BASELINE config 4)'
+                            % (SEED, n, ngpu),
+                'grid': [n, n, n], 'D': 6, 'step': 'one CG iteration',
+                'l2': 'working set per iteration and GPU (%.1f GB) exceeds the 126 MB L2; no flush needed'
+                      % (51*8*n**3/ngpu/1e9),
+                'parallelism': 'slab x%d: rank g owns x-planes [g*n/%d, (g+1)*n/%d); exchange mode %s'
+                               % (ngpu, ngpu, ngpu, slab)}
     return {'workload': '3-D linear elasticity (D=6 Mandel), random two-phase microstructure seed %d, 30%% inclusions, '
                         'GaNi %d^3, Galerkin CG (BASELINE config 3)' % (SEED, n),
             'grid': [n, n, n], 'D': 6, 'step': 'one CG iteration',
@@ -352,6 +362,169 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+# ----------------------------------------------------------------------------- GPU arm, N > 1: slab-decomposed solve
+def run_slab(args):
+    """BASELINE config 4: ONE elasticity solve at slab_n^3, x-planes split over the ranks.  `value` = voxel-DOFs
+    of the whole grid x CG iterations / max-over-ranks device time."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    from ffthompy_b200 import device as dev
+    import ffthompy_b200.projections as proj
+    from ffthompy_b200.slab import SlabGA, SlabLayout
+    dev.init(local)
+    n = args.slab_n
+    N = (n, n, n)
+    D = 6
+    nvox = float(n)**3
+    K, W = args.steps, max(args.warmup, 3)
+    lay = SlabLayout(N, world, rank)
+
+    def make_A():
+        # every rank draws only its own x-planes of the one-shot array (PCG64.advance: bit-identical, SURVEY 8d C4)
+        bg = np.random.PCG64(SEED)
+        bg.advance(lay.n0_off*n*n)
+        ph = np.random.Generator(bg).random((lay.n0l, n, n)) < 0.3
+        phase = torch.from_numpy(ph).to(dev.device()).to(torch.float64)
+        Cm = torch.from_numpy(elastic_mandel(1, 1)).to(dev.device())
+        Ci = torch.from_numpy(elastic_mandel(10, 5)).to(dev.device())
+        return (Cm[:, :, None, None, None]*(1-phase)+Ci[:, :, None, None, None]*phase).contiguous()
+
+    Ad = make_A()
+    _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3), NyqNul=True, tensor=True)
+    G = G1h+G1s
+    op = SlabGA(Ad, G, N, exchange=args.exchange)
+    shape = (D, lay.n0l, n, n)
+    E = dev.zeros(shape)
+    E[0] = -1.
+    B = op.apply(E)
+    del E
+    x0 = dev.zeros(shape)
+    st = op.cg_begin(B, x0)
+    op.cg_steps(st, 0.0, W)
+    sampler = ClockSampler(local)
+    op.exchanged_bytes = 0
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    launches0 = dev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    done = op.cg_steps(st, 0.0, K)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    assert done == K
+    launches = dev.launch_count()-launches0
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1), -float(launches)], dtype=torch.float64, device=dev.device())
+    dist.all_reduce(t[:1], op=dist.ReduceOp.MAX)          # device time, max over ranks
+    dist.all_reduce(t[1:], op=dist.ReduceOp.SUM)
+    ms_step = float(t[0].item())/K
+    launches_all = int(-t[1].item())
+    value = D*nvox*K/(float(t[0].item())*1e-3)
+    sent = op.exchanged_bytes/K
+    peak, peak_src = measured_peaks()
+
+    # ---- per-stage device time, every rank inside the same stage (barrier in front of each launch)
+    P = op.pitch
+    F = 8.*D*nvox/world
+    Fs = 16.*D*lay.n0l*n*P
+    alg = {1: F+1.*nvox/world+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
+    names = {1: 'S1 A.p + R2C (last axis)', 2: 'S2 C2C axis 1',
+             3: 'S3 C2C axis 0 + Green + inverse axis 0, fused with the exchange (remote loads/stores over NVLink)'
+                if op.mode == 'peer' else 'S3 C2C axis 0 + Green + inverse axis 0',
+             4: 'S4 inverse C2C axis 1', 5: 'S5 C2R (last axis) + <p,Ap>'}
+    stage_ms = {}
+    if op.mode in ('peer', 'packed'):
+        xin = dev.zeros(shape)
+        xin.normal_()
+        y = dev.zeros(shape)
+        for stg in (1, 2, 3, 4, 5):
+            ts = []
+            for rep in range(4):
+                dist.barrier()
+                op._barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                op._stage(stg, 0, xin, None, 0, y)
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            tt = torch.tensor([float(np.mean(ts[1:]))], dtype=torch.float64, device=dev.device())
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            stage_ms[stg] = float(tt.item())
+        del xin, y
+    B_iter = 15*8.*D*nvox+8.*21*nvox
+    roofline = {'bound': 'hbm', 'peak': peak, 'unit': 'GB/s', 'peak_source': peak_src, 'traffic': None,
+                'iteration': {'algorithmic_bytes': B_iter, 'achieved_GB/s_aggregate': B_iter/(ms_step*1e-3)/1e9,
+                              'frac_of_aggregate_peak': B_iter/(ms_step*1e-3)/1e9/(world*peak)},
+                'nvlink': {'GB_sent_per_gpu_per_iteration': sent/1e9, 'achieved_GB/s_per_gpu': sent/(ms_step*1e-3)/1e9,
+                           'peak_GB/s_per_direction': 900.0, 'frac': sent/(ms_step*1e-3)/900e9}}
+    if stage_ms:
+        dom = max(stage_ms, key=lambda k: stage_ms[k])
+        ach = alg[dom]/(stage_ms[dom]*1e-3)/1e9
+        roofline.update({'kernel': names[dom], 'achieved': ach, 'frac': ach/peak, 'algorithmic_bytes_per_launch': alg[dom],
+                         'stages': {names[k]: {'ms': stage_ms[k], 'GB/s_per_gpu': alg[k]/(stage_ms[k]*1e-3)/1e9,
+                                               'share_of_step': stage_ms[k]/ms_step} for k in stage_ms}})
+    else:
+        roofline.update({'kernel': 'whole iteration (chunk-pipelined exchange: stages overlap)',
+                         'achieved': B_iter/world/(ms_step*1e-3)/1e9, 'frac': B_iter/world/(ms_step*1e-3)/1e9/peak})
+    mode, nchunk = op.mode, op.nchunk
+
+    # ---- end to end with HOST buffers: pinned A slab -> device, operator set-up, solve to 1e-6, solution slab -> host
+    del st, B, x0
+    e2e = None
+    ok = torch.ones(1, device=dev.device())
+    try:
+        A_host = torch.empty(Ad.shape, dtype=torch.float64, pin_memory=True)
+        A_host.copy_(Ad)
+    except Exception:
+        ok.zero_()
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    del op, Ad
+    torch.cuda.empty_cache()
+    if ok.item() > 0:
+        torch.cuda.synchronize()
+        dist.barrier()
+        t0 = time.perf_counter()
+        A2 = A_host.to(dev.device(), non_blocking=True)
+        _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3), NyqNul=True, tensor=True)
+        op2 = SlabGA(A2, G1h+G1s, N, exchange=args.exchange)
+        E2 = dev.zeros(shape)
+        E2[0] = -1.
+        X, info = op2.cg(op2.apply(E2), dev.zeros(shape), tol=1e-6, maxiter=1000)
+        x_host = X.cpu()
+        torch.cuda.synchronize()
+        tt = torch.tensor([time.perf_counter()-t0], dtype=torch.float64, device=dev.device())
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = float(tt.item())
+        kit = info['kit']
+        e2e = {'value': D*nvox*kit/t_e2e, 'unit': 'voxel-DOF/s',
+               'h2d_bytes_per_step': int(world*A_host.numel()*8/kit), 'd2h_bytes_per_step': int(world*x_host.numel()*8/kit),
+               'cg_iterations': kit, 'seconds': t_e2e,
+               'what': 'SlabGA(A_slab).cg(tol 1e-6) on every rank: pinned-host coefficient slab uploaded, operator '
+                       'set-up (symmetric-memory rendezvous included), solve, solution slab downloaded; wall clock, '
+                       'max over ranks'}
+        del op2, A2, X
+    if rank == 0:
+        line = {'metric': 'cg_voxel_dof_per_s', 'value': value, 'unit': 'voxel-DOF/s',
+                'cg_iterations_per_s': 1e3/ms_step, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': ms_step,
+                'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': workload_config(n, world, 'gpu', slab='%s (chunks %d)' % (mode, nchunk)),
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_all, 'roofline': roofline,
+                'note': 'strong scaling over N = 2, 4, 8 at the fixed 512^3 grid; the N = 1 line is the 256^3 '
+                        'single-GPU workload (BASELINE config 3). value is size-normalised (voxel-DOF/s).'}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -359,9 +532,15 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--n', type=int, default=256)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--mode', default='slab', choices=['slab', 'replicas'],
+                    help='N > 1: one slab-decomposed solve (default) or N independent replicas')
+    ap.add_argument('--slab-n', type=int, default=512, help='grid size of the slab-decomposed solve')
+    ap.add_argument('--exchange', default=None, help='slab exchange mode (default: best available)')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)
+    elif int(os.environ.get('WORLD_SIZE', '1')) > 1 and args.mode == 'slab':
+        run_slab(args)
     else:
         run_ours(args)
 

@@ -203,7 +203,8 @@ template <int N, int D, int TRW, int ALAY, int NT, typename Store>
 __device__ __forceinline__ void s1_sigma_phase(const double* __restrict__ A, const unsigned char* __restrict__ phase,
                                                const double* slut, const Lut2C& lutc, double* __restrict__ p,
                                                const double* __restrict__ r, double beta, int pupdate, int64_t row0,
-                                               int64_t n, Store store) {
+                                               int64_t n, Store store, double* __restrict__ xacc = nullptr,
+                                               double alpha = 0.0) {
     // phase 0: sigma = A p on TRW x N voxels, two voxels per thread and step (16-byte accesses)
     for (int v = threadIdx.x; v < TRW * (N / 2); v += NT) {
         const int row = v / (N / 2), i2 = 2 * (v - row * (N / 2));
@@ -220,6 +221,11 @@ __device__ __forceinline__ void s1_sigma_phase(const double* __restrict__ A, con
             double2 q = *reinterpret_cast<const double2*>(p + (size_t)jj * n + gv);
             if (pupdate) {
                 const double2 rr = *reinterpret_cast<const double2*>(r + (size_t)jj * n + gv);
+                if (xacc) {  // deferred x += alpha p of the previous iteration (solver.py:127): p is in registers anyway
+                    double2* xp = reinterpret_cast<double2*>(xacc + (size_t)jj * n + gv);
+                    const double2 xv = *xp;
+                    *xp = make_double2(xv.x + alpha * q.x, xv.y + alpha * q.y);
+                }
                 q = make_double2(rr.x + beta * q.x, rr.y + beta * q.y);
                 *reinterpret_cast<double2*>(p + (size_t)jj * n + gv) = q;
             }
@@ -260,7 +266,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     k_fwd_last_fast(const double* __restrict__ A, const unsigned char* __restrict__ phase,
                     const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
                     const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
-                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
+                    double* __restrict__ xacc) {
     constexpr int R1 = FastCfg<N>::R1, R2 = FastCfg<N>::R2, TPL = FastCfg<N>::TPL;
     constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 16;
     constexpr int NT = NP * TPL;
@@ -271,6 +278,7 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     const int64_t n = nrows * N;  // voxels per component
     const double beta = pupdate ? scal[3] : 0.0;
+    const double alpha = (pupdate && xacc) ? scal[2] : 0.0;
     __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
     if (ALAY == 2) {
         for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
@@ -281,7 +289,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
                                             double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
                                             dst[pidx(i2)] = s0;
                                             dst[pidx(i2 + 1)] = s1;
-                                        });
+                                        },
+                                        xacc, alpha);
     __syncthreads();
     const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
     double* lre = zre + pr * NPAD;
@@ -614,7 +623,8 @@ __global__ void __launch_bounds__(D * T * 16) k_mid_copy_only(cplx* __restrict__
 // global memory.  Two such CTAs fit on one SM (registers and shared memory), so the global-load
 // phase of one overlaps the FP64 / shared-memory phases of the other.
 template <int N, int T, int KIND, int DIM, int CR>
-__global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) / CR) * T * FastCfg<N>::TPL, 2)
+__global__ void __launch_bounds__((((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2) / CR) * T * FastCfg<N>::TPL,
+                                  (T > 4) ? 1 : 2)
     k_mid_green_2r(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh, int pitch,
                    int tpr, int col0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
@@ -870,6 +880,89 @@ __global__ void __launch_bounds__(256) k_c2c_gen3(const cplx* __restrict__ in, c
     }
 }
 
+// ------------------------------------------------------------------ strided complex axis, three register passes
+// N = R1*R2*R3 (512 = 8*8*8, 1024 = 8*8*16, 2048 = 8*16*16): the register-resident scheme of k_c2c_fast with one
+// more pass.  Every thread owns one butterfly per pass; pass 1 loads its R1 inputs straight from global memory
+// (R1 independent 16-byte loads in flight per thread), two exchanges through shared memory, pass 3 stores straight
+// back in natural order.  With M = N/R1:
+//   pass 1, thread j < N/R1        : a_q = DFT_R1(x[j + r*M]) * w_N^(q j)                -> smem[q*M + j]
+//   pass 2, thread (q, j' < R3)    : c_q2 = DFT_R2(smem[q*M + j' + r*R3]) * w_N^(R1 j' q2) -> smem[q*M + q2*R3 + j']  (in place)
+//   pass 3, thread u = q + R1*q2   : X[u + R1*R2*k] = DFT_R3(smem[q*M + q2*R3 + j'])[k]   -> global
+// smem is [N][T] complex; T = 8 makes every row one 128-byte line, so all three access patterns are conflict free.
+template <int N>
+struct Fac3r;
+template <>
+struct Fac3r<256> {
+    static constexpr int R1 = 8, R2 = 8, R3 = 4;
+};
+template <>
+struct Fac3r<512> {
+    static constexpr int R1 = 8, R2 = 8, R3 = 8;
+};
+template <>
+struct Fac3r<1024> {
+    static constexpr int R1 = 8, R2 = 8, R3 = 16;
+};
+template <>
+struct Fac3r<2048> {
+    static constexpr int R1 = 8, R2 = 16, R3 = 16;
+};
+template <int N>
+struct Reg3Cfg {
+    static constexpr int R1 = Fac3r<N>::R1, R2 = Fac3r<N>::R2, R3 = Fac3r<N>::R3;
+    static constexpr int B1 = N / R1, B2 = N / R2, B3 = N / R3;
+    static constexpr int TPL = (B1 > B2 ? (B1 > B3 ? B1 : B3) : (B2 > B3 ? B2 : B3));
+};
+
+template <int N, int T, bool INV>
+__global__ void __launch_bounds__(T* Reg3Cfg<N>::TPL) k_c2c_reg3(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                                  const cplx* __restrict__ tw, int64_t inner, int ntile,
+                                                                  int tile0, double scale) {
+    constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
+    constexpr int M = N / R1;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [N][T]
+    const int t = threadIdx.x % T, u = threadIdx.x / T;
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t base = o * N * inner + (int64_t)(tile0 + tile) * T + t;
+    if (u < Reg3Cfg<N>::B1) {
+        cplx v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = in[base + (int64_t)(u + r * M) * inner];
+        Bfly<R1, INV>::run(v);
+#pragma unroll
+        for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, INV));
+#pragma unroll
+        for (int q = 0; q < R1; ++q) smc[(q * M + u) * T + t] = v[q];
+    }
+    __syncthreads();
+    if (u < Reg3Cfg<N>::B2) {
+        const int q = u / R3, jp = u - q * R3;
+        cplx* sp = smc + (q * M + jp) * T + t;
+        cplx v[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = sp[r * R3 * T];
+        Bfly<R2, INV>::run(v);
+#pragma unroll
+        for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, INV));
+#pragma unroll
+        for (int q2 = 0; q2 < R2; ++q2) sp[q2 * R3 * T] = v[q2];
+    }
+    __syncthreads();
+    if (u < Reg3Cfg<N>::B3) {
+        const int q = u % R1, q2 = u / R1;
+        const cplx* sp = smc + (q * M + q2 * R3) * T + t;
+        cplx v[R3];
+#pragma unroll
+        for (int jp = 0; jp < R3; ++jp) v[jp] = sp[jp * T];
+        Bfly<R3, INV>::run(v);
+#pragma unroll
+        for (int k = 0; k < R3; ++k)
+            out[base + (int64_t)(u + R1 * R2 * k) * inner] = make_double2(v[k].x * scale, v[k].y * scale);
+    }
+}
+
 // axis 0 + G^ through the generic routine: data [D][N][inner], tile of T inner positions
 template <int N, int T, int KIND, int DIM>
 __global__ void __launch_bounds__(384) k_mid_green_gen3(cplx* __restrict__ data, const cplx* __restrict__ tw,
@@ -930,13 +1023,15 @@ __global__ void __launch_bounds__(256)
     k_fwd_last_gen3(const double* __restrict__ A, const unsigned char* __restrict__ phase,
                     const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
                     const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
-                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch) {
+                    cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
+                    double* __restrict__ xacc) {
     constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [N + N/16][NP]
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     const int64_t n = nrows * N;
     const double beta = pupdate ? scal[3] : 0.0;
+    const double alpha = (pupdate && xacc) ? scal[2] : 0.0;
     __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
     if (ALAY == 2) {
         for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
@@ -948,7 +1043,8 @@ __global__ void __launch_bounds__(256)
                                             const int pr = L >> 1, part = L & 1;
                                             bd[2 * (pidx(i2) * NP + pr) + part] = s0;
                                             bd[2 * (pidx(i2 + 1) * NP + pr) + part] = s1;
-                                        });
+                                        },
+                                        xacc, alpha);
     __syncthreads();
     smem_fft_inplace<N, false>(buf, NP, tw);
     for (int it = threadIdx.x; it < NL * pitch; it += NT) {
@@ -1228,7 +1324,7 @@ __global__ void __launch_bounds__(256, 2)
     k_fwd_last_rt(const double* __restrict__ A, const unsigned char* __restrict__ phase, const double* __restrict__ lut,
                   const Lut2C lutc, int nphase, double* __restrict__ p, const double* __restrict__ r,
                   const double* __restrict__ scal, int pupdate, cplx* __restrict__ spec, const cplx* __restrict__ tw,
-                  RtPlan P, int64_t nrows, int nh, int pitch) {
+                  RtPlan P, int64_t nrows, int nh, int pitch, double* __restrict__ xacc) {
     constexpr int NL = D * TRW, NP = NL / 2, NT = 256;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     cplx* buf = reinterpret_cast<cplx*>(fh_smem_raw);  // [npr][NP]
@@ -1237,6 +1333,7 @@ __global__ void __launch_bounds__(256, 2)
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     const int64_t n = nrows * N;
     const double beta = pupdate ? scal[3] : 0.0;
+    const double alpha = (pupdate && xacc) ? scal[2] : 0.0;
     __shared__ double slut[(ALAY == 2) ? 16 * D * D : 1];
     if (ALAY == 2) {
         for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
@@ -1255,6 +1352,7 @@ __global__ void __launch_bounds__(256, 2)
             if (live) {
                 q = p[(size_t)jj * n + gv];
                 if (pupdate) {
+                    if (xacc) xacc[(size_t)jj * n + gv] = xacc[(size_t)jj * n + gv] + alpha * q;  // deferred x += alpha p
                     q = r[(size_t)jj * n + gv] + beta * q;
                     p[(size_t)jj * n + gv] = q;
                 }

@@ -17,6 +17,7 @@
 #include "fh_plan.cuh"
 #include "fh_green.cuh"
 #include "fh_fast.cuh"
+#include "fh_reg3.h"
 #include "../../include/ffthom_b200.h"
 #include <stdlib.h>
 #include <string.h>
@@ -60,6 +61,7 @@ struct fh_ga {
     // CG state (fh_cg_begin / fh_cg_steps)
     int64_t kit;
     int have_beta;
+    double* xacc;    // non-null inside fh_cg_steps: S1 applies the deferred x += alpha p while it has p in registers
     int last_npart;  // partial sums left in `part` by the last stage-5 launch
     // row range of the next S1 / S5 launch (chunked slab pipeline); row_cnt = 0 means all rows
     int64_t row_beg, row_cnt;
@@ -94,6 +96,10 @@ static RowRange row_range(const fh_ga* op, int TRW, bool round_up) {
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
+}
+static bool use_reg3() {
+    static const int v = env_int("FH_REG3", 1);
+    return v != 0;
 }
 
 // ------------------------------------------------------------------ generic pieces
@@ -267,8 +273,29 @@ static int launch_c2c_gen3_NT(const cplx* tw, cplx* data, int64_t outer, int64_t
     return FH_OK;
 }
 
+template <int N, int T>
+static int launch_c2c_reg3_NT(const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv) {
+    const size_t smem = (size_t)N * T * sizeof(cplx);
+    const int ntile = (int)(inner / T);
+    const unsigned nblk = (unsigned)(outer * ntile);
+    const int nt = T * Reg3Cfg<N>::TPL;
+    int rc;
+    if (inv) {
+        if ((rc = smem_attr(k_c2c_reg3<N, T, true>, smem))) return rc;
+        k_c2c_reg3<N, T, true><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, 0, 1.0);
+    } else {
+        if ((rc = smem_attr(k_c2c_reg3<N, T, false>, smem))) return rc;
+        k_c2c_reg3<N, T, false><<<nblk, nt, smem, fh_stream()>>>(data, data, tw, inner, ntile, 0, 1.0);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+
 static int launch_c2c_fast(int N, const cplx* tw, cplx* data, int64_t outer, int64_t inner, bool inv, int col0 = 0,
                            int ncols = 0) {
+    static const int reg3 = env_int("FH_REG3", 1);  // register-resident three-pass kernels for 512 / 1024 (0: generic smem)
+    if (reg3 && N == 512) return launch_c2c_reg3_NT<512, 8>(tw, data, outer, inner, inv);
+    if (reg3 && N == 1024) return launch_c2c_reg3_NT<1024, 8>(tw, data, outer, inner, inv);
     switch (N) {
         case 16: return launch_c2c_gen3_NT<16, 8>(tw, data, outer, inner, inv);
         case 32: return launch_c2c_gen3_NT<32, 8>(tw, data, outer, inner, inv);
@@ -350,6 +377,11 @@ template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
+    if (use_reg3() && fh_reg3_mid_len(N)) {  // three-pass register kernels (fh_reg3.cu decides which lengths)
+        const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
+        if (inner % 8 == 0)
+            return fh_reg3_mid_green(N, KIND, DIM, op->specT, op->plan->ax[0].tw, op->g, inner, op->plan->nh, op->pitch);
+    }
     if (N == 16) return launch_mid_gen3_NT<16, 4, KIND, DIM>(op);
     if (N == 32) return launch_mid_gen3_NT<32, 4, KIND, DIM>(op);
     if (N == 512) return launch_mid_gen3_NT<512, 2, KIND, DIM>(op);
@@ -365,6 +397,9 @@ static int launch_mid_fast(fh_ga* op) {
         k_mid_copy_only<256, 4, D><<<(unsigned)(inner / 4), D * 4 * 16, smem, fh_stream()>>>(op->specT, inner);
         FH_LAUNCH_CHECK();
         return FH_OK;
+    }
+    if (op->mid_pipe == 3 && N == 256) {  // 8 columns per tile (128-byte segments), one 384-thread CTA per SM
+        if constexpr (KIND == FH_GREEN_ELASTIC && DIM == 3) return launch_mid_2r_NT<256, 8, KIND, DIM, 2>(op);
     }
     if (op->mid_pipe == 2 && T == 4) {
         constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
@@ -406,9 +441,8 @@ static int launch_fwd_last_NTA(fh_ga* op, double* p, const double* r, int pupdat
     if ((rc = smem_attr(k_fwd_last_fast<N, D, TRW, ALAY>, smem))) return rc;
     k_fwd_last_fast<N, D, TRW, ALAY><<<nblk, nt, smem, fh_stream()>>>(
         op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
-        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so,
-                                                                       pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
-                                                                       op->pitch);
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so, pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
+        op->pitch, op->xacc ? op->xacc + rr_.ro : nullptr);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -539,8 +573,8 @@ static int launch_fwd_last_rtA(fh_ga* op, double* p, const double* r, int pupdat
     if ((rc = smem_attr(k_fwd_last_rt<D, TRW, ALAY>, smem))) return rc;
     k_fwd_last_rt<D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(
         op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
-        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so, pl->ax[ax].tw, P,
-                                                                  op->nrows, pl->nh, op->pitch);
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so, pl->ax[ax].tw, P, op->nrows, pl->nh,
+        op->pitch, op->xacc ? op->xacc + rr_.ro : nullptr);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -603,9 +637,8 @@ static int launch_fwd_last_g3A(fh_ga* op, double* p, const double* r, int pupdat
     if ((rc = smem_attr(k_fwd_last_gen3<N, D, TRW, ALAY>, smem))) return rc;
     k_fwd_last_gen3<N, D, TRW, ALAY><<<nblk, 256, smem, fh_stream()>>>(
         op->A + rr_.ro, op->phase ? op->phase + rr_.ro : nullptr, op->lut, op->lutc, op->nphase, p + rr_.ro,
-        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so,
-                                                                       pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
-                                                                       op->pitch);
+        r ? r + rr_.ro : nullptr, op->scal, pupdate, op->spec + rr_.so, pl->ax[pl->dim - 1].tw, op->nrows, pl->nh,
+        op->pitch, op->xacc ? op->xacc + rr_.ro : nullptr);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -691,11 +724,64 @@ static int launch_inv_last_gen3(fh_ga* op, double* y, const double* pdot, int* n
         return fh_set_error(FH_ERR_UNSUPPORTED, "no fast last-axis kernel"); \
     } while (0)
 
+// register-resident three-pass kernels (fh_reg3.cu) for the lengths they cover; FH_REG3=0 falls back to the
+// generic shared-memory routine
+static int launch_fwd_last_reg3(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    const fh_plan* pl = op->plan;
+    const RowRange rr_ = row_range(op, op->trw, false);
+    Reg3LastArgs a;
+    a.A = op->A + rr_.ro;
+    a.phase = op->phase ? op->phase + rr_.ro : nullptr;
+    a.lut = op->lut;
+    a.lutc = &op->lutc;
+    a.nphase = op->nphase;
+    a.alay = !withA ? -1 : (op->a_mode == 2 ? ((op->nphase <= 2 && op->D * op->D <= 36) ? 3 : 2) : (op->a_mode == 1 ? 1 : 0));
+    a.p = p + rr_.ro;
+    a.r = r ? r + rr_.ro : nullptr;
+    a.scal = op->scal;
+    a.pupdate = pupdate;
+    a.spec = op->spec + rr_.so;
+    a.tw = pl->ax[pl->dim - 1].tw;
+    a.nrows = op->nrows;
+    a.nh = pl->nh;
+    a.pitch = op->pitch;
+    a.xacc = op->xacc ? op->xacc + rr_.ro : nullptr;
+    a.nblk = rr_.nblk;
+    return fh_reg3_fwd_last(pl->N[pl->dim - 1], op->D, op->trw, a);
+}
+static int launch_inv_last_reg3(fh_ga* op, double* y, const double* pdot, int* npart) {
+    const fh_plan* pl = op->plan;
+    const RowRange rr_ = row_range(op, op->trw, false);
+    if (pdot && rr_.pb + rr_.nblk > GA_MAXPART)
+        return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", rr_.nblk);
+    Reg3InvArgs a;
+    a.spec = op->spec + rr_.so;
+    a.y = y + rr_.ro;
+    a.pdot = pdot ? pdot + rr_.ro : nullptr;
+    a.part = op->part + rr_.pb;
+    a.tw = pl->ax[pl->dim - 1].tw;
+    a.nrows = op->nrows;
+    a.nh = pl->nh;
+    a.pitch = op->pitch;
+    a.scale = 1.0 / (double)pl->nreal;
+    a.nblk = rr_.nblk;
+    int rc;
+    if ((rc = fh_reg3_inv_last(pl->N[pl->dim - 1], op->D, op->trw, a))) return rc;
+    if (npart) *npart = (int)(rr_.pb + rr_.nblk);
+    return FH_OK;
+}
+static bool reg3_last_ok(const fh_ga* op) {
+    const int nl = op->plan->N[op->plan->dim - 1];
+    return use_reg3() && fh_reg3_last_len(nl) && (op->D == 6 || op->D == 3 || op->D == 2) &&
+           op->trw == ((op->D == 6) ? 2 : 4);
+}
 static int launch_fwd_last_fast(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    if (reg3_last_ok(op)) return launch_fwd_last_reg3(op, p, r, pupdate, withA);
     if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_fwd_last_gen3(op, p, r, pupdate, withA);
     FH_LAST_DISPATCH(launch_fwd_last_NT, op, p, r, pupdate, withA);
 }
 static int launch_inv_last_fast(fh_ga* op, double* y, const double* pdot, int* npart) {
+    if (reg3_last_ok(op)) return launch_inv_last_reg3(op, y, pdot, npart);
     if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_inv_last_gen3(op, y, pdot, npart);
     FH_LAST_DISPATCH(launch_inv_last_NT, op, y, pdot, npart);
 }
@@ -1061,6 +1147,35 @@ __global__ void k_cg_update1(int64_t n, double* __restrict__ x, double* __restri
     }
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// deferred-x variant of the update: r -= alpha Ap ; partial r.r  (x += alpha p is applied by the next S1,
+// which holds p in registers anyway: one full-field read less per iteration)
+__global__ void k_cg_update_r(int64_t n2, double2* __restrict__ r, const double2* __restrict__ Ap,
+                              const double* __restrict__ scal, double* __restrict__ part) {
+    __shared__ double red[32];
+    const double alpha = scal[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 rv = r[i], av = Ap[i];
+        const double2 v = make_double2(rv.x - alpha * av.x, rv.y - alpha * av.y);
+        r[i] = v;
+        acc += v.x * v.x;
+        acc += v.y * v.y;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+// x += alpha p  (flush of the deferred update after the last iteration: scal[2] and p are still that iteration's)
+__global__ void k_cg_xflush(int64_t n2, double2* __restrict__ x, const double2* __restrict__ p,
+                            const double* __restrict__ scal) {
+    const double alpha = scal[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 xv = x[i], pv = p[i];
+        x[i] = make_double2(xv.x + alpha * pv.x, xv.y + alpha * pv.y);
+    }
 }
 
 // p = r + beta p   (solver.py:132)
@@ -1589,9 +1704,12 @@ extern "C" int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, 
 // up to `nsteps` CG iterations (solver.py:123-136), stopping early when norm_res <= tol.
 // Per iteration: 5 pipeline kernels (S1 carries p = r + beta p, S5 carries <p,Ap>), the x/r update
 // with <r,r>, two single-CTA scalar kernels, and one 8-byte read-back of the residual norm.
-extern "C" int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
-                           double* norm_res_host, double* hist_host) {
-    FH_REQUIRE(op && x && vecs && done_host && norm_res_host, "fh_cg_steps: null argument");
+// Deferred x update (default; FH_XDEFER=0 disables): iteration k leaves x += alpha_k p_k pending; S1 of iteration
+// k+1 applies it before it overwrites p (same expression, same rounding), and the loop flushes the last one
+// before it returns.  Needs an S1 kernel that carries the p update (fast / run-time-length paths) and an
+// even element count.
+static int cg_steps_impl(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
+                         double* norm_res_host, double* hist_host, int64_t hist_cap) {
     const int64_t n = (int64_t)op->D * op->nloc;
     const double inv = 1.0 / (double)op->plan->nreal;
     double* r = vecs;
@@ -1602,28 +1720,49 @@ extern "C" int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64
     int rc;
     double norm_res = *norm_res_host;
     int64_t done = 0;
+    static const int want_defer = env_int("FH_XDEFER", 1);
+    const bool defer = want_defer && n % 2 == 0 && (op->fast_last || op->rt_ok[op->plan->dim - 1]);
+    bool pending = false;  // x += alpha p of the last finished iteration not applied yet
     while (norm_res > tol && done < nsteps) {
         int np = 0;
-        if ((rc = ga_matvec(op, p, r, op->have_beta, Ap, 1, &np))) return rc;
+        op->xacc = pending ? x : NULL;
+        rc = ga_matvec(op, p, r, op->have_beta, Ap, 1, &np);
+        op->xacc = NULL;
+        if (rc) return rc;
+        pending = false;
         k_cg_scal<<<1, GA_NT, 0, s>>>(np, op->part, op->scal, inv, 1);
         FH_LAUNCH_CHECK();
-        if (n % 2 == 0)
+        if (defer) {
+            k_cg_update_r<<<g, GA_NT, 0, s>>>(n / 2, (double2*)r, (const double2*)Ap, op->scal, op->part);
+            pending = true;
+        } else if (n % 2 == 0) {
             k_cg_update<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap,
                                             op->scal, op->part);
-        else
+        } else {
             k_cg_update1<<<g, GA_NT, 0, s>>>(n, x, r, p, Ap, op->scal, op->part);
+        }
         FH_LAUNCH_CHECK();
         k_cg_scal<<<1, GA_NT, 0, s>>>((int)g, op->part, op->scal, inv, 2);
         FH_LAUNCH_CHECK();
         op->have_beta = 1;  // P = R + beta P is folded into the next S1
         if ((rc = read_norm(op, &norm_res))) return rc;
-        if (hist_host) hist_host[done] = norm_res;
+        if (hist_host && done < hist_cap) hist_host[done] = norm_res;
         ++done;
         ++op->kit;
+    }
+    if (pending) {
+        k_cg_xflush<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (const double2*)p, op->scal);
+        FH_LAUNCH_CHECK();
     }
     *done_host = done;
     *norm_res_host = norm_res;
     return FH_OK;
+}
+
+extern "C" int fh_cg_steps(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
+                           double* norm_res_host, double* hist_host) {
+    FH_REQUIRE(op && x && vecs && done_host && norm_res_host, "fh_cg_steps: null argument");
+    return cg_steps_impl(op, x, vecs, tol, nsteps, done_host, norm_res_host, hist_host, nsteps);
 }
 
 extern "C" int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t maxiter, double* vecs,
@@ -1636,13 +1775,9 @@ extern "C" int fh_cg(fh_ga* op, const double* B, double* x, double tol, int64_t 
     if ((rc = fh_cg_begin(op, B, x, vecs, &norm_res))) return rc;
     if (hist_host && hist_cap > 0) hist_host[0] = norm_res;
     int64_t kit = 0;
-    while (norm_res > tol && kit < maxiter) {
-        int64_t done = 0;
-        double h = 0.0;
-        if ((rc = fh_cg_steps(op, x, vecs, tol, 1, &done, &norm_res, &h))) return rc;
-        kit += done;
-        if (hist_host && kit < hist_cap) hist_host[kit] = norm_res;
-    }
+    if ((rc = cg_steps_impl(op, x, vecs, tol, maxiter, &kit, &norm_res, (hist_host && hist_cap > 1) ? hist_host + 1 : NULL,
+                            hist_cap - 1)))
+        return rc;
     *kit_host = kit;
     *norm_res_host = (kit == 0) ? 0.0 : norm_res;  // solver.py:137-138
     return FH_OK;

@@ -118,6 +118,14 @@ __device__ __forceinline__ void green_elastic_real(const GreenDesc& g, const dou
     } else {
         Se[2] = s2 * (n[0] * w[1] + w[0] * n[1]);
     }
+    if (g.cI == 0.0 && g.cL == 0.0 && g.cW == 0.0 && g.cS == 1.0 && g.scale == 1.0) {
+        // the strain projector G1h + G1s (and G1s alone) on the solve grid: the dropped terms are exact zeros and
+        // multiplications by one, so this shorter form rounds exactly like the general one below
+        const double cHn1 = g.cH * nw;
+#pragma unroll
+        for (int m = 0; m < D; ++m) e[m] = Se[m] + cHn1 * v[m];
+        return;
+    }
     const double cHn = g.cH * nw + g.cW * tr;          // multiplies v
     const double cdiag = g.cL * tr / DIM + g.cW * nw;  // multiplies Mandel(I)
 #pragma unroll

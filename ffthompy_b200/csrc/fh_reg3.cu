@@ -1,0 +1,96 @@
+// fh_reg3.cu — launchers of the register-resident three-pass kernels (fh_reg3.cuh) for axis length 512.
+// Internal C++ interface (fh_reg3.h) used by the fused operator in fh_fused.cu; nothing here is part of the C ABI.
+#include "fh_reg3.cuh"
+#include "fh_reg3.h"
+#include <stdlib.h>
+
+template <typename K>
+static int reg3_smem_attr(K kernel, size_t bytes) {
+    if (bytes > (size_t)fh_max_smem_optin())
+        return fh_set_error(FH_ERR_UNSUPPORTED, "three-pass kernel needs %zu bytes of shared memory", bytes);
+    FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return FH_OK;
+}
+
+static int reg3_env(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return s ? atoi(s) : dflt;
+}
+bool fh_reg3_last_len(int n) { return n == 512; }
+// axis-0 kernel: 512 always; 256 (8 columns per tile, 128-byte segments) when FH_MID256_REG3=1
+bool fh_reg3_mid_len(int n) {
+    static const int m256 = reg3_env("FH_MID256_REG3", 0);
+    return n == 512 || (n == 256 && m256);
+}
+
+template <int N, int D, int TRW, int ALAY>
+static int fwd_last_A(const Reg3LastArgs& a) {
+    constexpr int NP = D * TRW / 2, NPAD = N + N / 8;
+    const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
+    int rc;
+    if ((rc = reg3_smem_attr(k_fwd_last_reg3<N, D, TRW, ALAY>, smem))) return rc;
+    k_fwd_last_reg3<N, D, TRW, ALAY><<<a.nblk, NP * Reg3Cfg<N>::TPL, smem, fh_stream()>>>(
+        a.A, a.phase, a.lut, *a.lutc, a.nphase, a.p, a.r, a.scal, a.pupdate, a.spec, a.tw, a.nrows, a.nh, a.pitch,
+        a.xacc);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+template <int N, int D, int TRW>
+static int fwd_last_D(const Reg3LastArgs& a) {
+    switch (a.alay) {
+        case -1: return fwd_last_A<N, D, TRW, -1>(a);
+        case 0: return fwd_last_A<N, D, TRW, 0>(a);
+        case 1: return fwd_last_A<N, D, TRW, 1>(a);
+        case 2: return fwd_last_A<N, D, TRW, 2>(a);
+        case 3: return fwd_last_A<N, D, TRW, 3>(a);
+    }
+    return fh_set_error(FH_ERR_ARG, "three-pass S1: bad coefficient layout %d", a.alay);
+}
+int fh_reg3_fwd_last(int N, int D, int trw, const Reg3LastArgs& a) {
+    if (N == 512 && D == 6 && trw == 2) return fwd_last_D<512, 6, 2>(a);
+    if (N == 512 && D == 3 && trw == 4) return fwd_last_D<512, 3, 4>(a);
+    if (N == 512 && D == 2 && trw == 4) return fwd_last_D<512, 2, 4>(a);
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass last-axis kernel for N=%d D=%d TRW=%d", N, D, trw);
+}
+
+template <int N, int D, int TRW>
+static int inv_last_D(const Reg3InvArgs& a) {
+    constexpr int NP = D * TRW / 2, NPAD = N + N / 8;
+    const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
+    int rc;
+    if ((rc = reg3_smem_attr(k_inv_last_reg3<N, D, TRW>, smem))) return rc;
+    k_inv_last_reg3<N, D, TRW><<<a.nblk, NP * Reg3Cfg<N>::TPL, smem, fh_stream()>>>(a.spec, a.y, a.pdot, a.part, a.tw,
+                                                                                   a.nrows, a.nh, a.pitch, a.scale);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
+    if (N == 512 && D == 6 && trw == 2) return inv_last_D<512, 6, 2>(a);
+    if (N == 512 && D == 3 && trw == 4) return inv_last_D<512, 3, 4>(a);
+    if (N == 512 && D == 2 && trw == 4) return inv_last_D<512, 2, 4>(a);
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass last-axis kernel for N=%d D=%d TRW=%d", N, D, trw);
+}
+
+template <int N, int T, int KIND, int DIM>
+static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch) {
+    constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
+    constexpr int NT = 768;
+    const size_t smem = (size_t)D * (N + N / 8) * T * sizeof(cplx);
+    int rc;
+    if ((rc = reg3_smem_attr(k_mid_green_reg3<N, T, KIND, DIM, NT>, smem))) return rc;
+    k_mid_green_reg3<N, T, KIND, DIM, NT><<<(unsigned)(inner / T), NT, smem, fh_stream()>>>(data, tw, g, inner, nh, pitch);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                      int pitch) {
+    if (N == 256 && inner % 8 == 0 && kind == FH_GREEN_ELASTIC && dim == 3)
+        return mid_KD<256, 8, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch);
+    if (N != 512 || inner % 4 != 0)
+        return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass axis-0 kernel for N0=%d inner=%lld", N, (long long)inner);
+    if (kind == FH_GREEN_SCALAR)
+        return (dim == 3) ? mid_KD<512, 4, FH_GREEN_SCALAR, 3>(data, tw, g, inner, nh, pitch)
+                          : mid_KD<512, 4, FH_GREEN_SCALAR, 2>(data, tw, g, inner, nh, pitch);
+    return (dim == 3) ? mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch)
+                      : mid_KD<512, 4, FH_GREEN_ELASTIC, 2>(data, tw, g, inner, nh, pitch);
+}

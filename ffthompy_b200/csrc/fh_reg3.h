@@ -1,0 +1,39 @@
+// fh_reg3.h — internal interface between fh_fused.cu and the three-pass kernels of fh_reg3.cu (not C ABI).
+#pragma once
+#include "fh_green.cuh"
+struct Lut2C;
+
+struct Reg3LastArgs {  // S1 (k_fwd_last_reg3): pointers already offset to the first row of the launch
+    const double* A;
+    const unsigned char* phase;
+    const double* lut;
+    const Lut2C* lutc;
+    int nphase, alay;
+    double* p;
+    const double* r;
+    const double* scal;
+    int pupdate;
+    cplx* spec;
+    const cplx* tw;
+    int64_t nrows;
+    int nh, pitch;
+    double* xacc;
+    unsigned nblk;
+};
+struct Reg3InvArgs {  // S5 (k_inv_last_reg3)
+    const cplx* spec;
+    double* y;
+    const double* pdot;
+    double* part;
+    const cplx* tw;
+    int64_t nrows;
+    int nh, pitch;
+    double scale;
+    unsigned nblk;
+};
+bool fh_reg3_last_len(int n);
+bool fh_reg3_mid_len(int n);
+int fh_reg3_fwd_last(int N, int D, int trw, const Reg3LastArgs& a);
+int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a);
+int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                      int pitch);

@@ -351,9 +351,9 @@ class SlabGA(object):
         L.check(lib.fh_cgd_scal(self.handle, dev.ptr(self.sums), mode, C.byref(norm) if want_norm else None))
         return norm.value
 
-    def cg(self, B, x0, tol=1e-6, maxiter=1000):
-        """general/solver.py:80-139 on the slab; alpha, beta, rr stay on the device, the host reads only
-        ||r|| (8 bytes) per iteration for the stop test.  Returns x (device, local slab), info."""
+    def cg_begin(self, B, x0):
+        """initial residual of general/solver.py:80-100 (one operator application on x0); returns the
+        CG state (x, vecs, r, p, Ap, have_beta, norm_res) that `cg_steps` advances."""
         from . import ops
         L, lib, dev = self.L, self.dev.lib(), self.dev
         n = self.D*self.nloc
@@ -364,14 +364,30 @@ class SlabGA(object):
         self.apply(x, Ap)
         L.check(lib.fh_cgd_init(self.handle, dev.ptr(B), dev.ptr(vecs)))
         norm_res = self._global_scalar(0, True)
-        kit, have_beta = 0, 0
-        hist = [norm_res]
-        while norm_res > tol and kit < maxiter:
-            kit += 1
-            self.apply(p, Ap, r=r, pupdate=have_beta)     # p = r + beta p folded into S1; <p,Ap> into S5
+        return {'x': x, 'vecs': vecs, 'r': r, 'p': p, 'Ap': Ap, 'have_beta': 0, 'norm_res': norm_res, 'kit': 0,
+                'hist': [norm_res]}
+
+    def cg_steps(self, st, tol, nsteps):
+        """at most `nsteps` further CG iterations (stops early once ||r|| <= tol, the reference's absolute
+        test); alpha, beta, rr stay on the device, the host reads only ||r|| (8 bytes) per iteration.
+        Returns the number of iterations done."""
+        L, lib, dev = self.L, self.dev.lib(), self.dev
+        done = 0
+        while st['norm_res'] > tol and done < nsteps:
+            done += 1
+            self.apply(st['p'], st['Ap'], r=st['r'], pupdate=st['have_beta'])  # p = r + beta p folded into S1
             self._global_scalar(1, False)
-            L.check(lib.fh_cgd_update(self.handle, dev.ptr(x), dev.ptr(vecs)))
-            norm_res = self._global_scalar(2, True)
-            have_beta = 1
-            hist.append(norm_res)
-        return x, {'kit': kit, 'norm_res': norm_res if kit > 0 else 0, 'norm_res_log': np.array(hist)}
+            L.check(lib.fh_cgd_update(self.handle, dev.ptr(st['x']), dev.ptr(st['vecs'])))
+            st['norm_res'] = self._global_scalar(2, True)
+            st['have_beta'] = 1
+            st['hist'].append(st['norm_res'])
+        st['kit'] += done
+        return done
+
+    def cg(self, B, x0, tol=1e-6, maxiter=1000):
+        """general/solver.py:80-139 on the slab.  Returns x (device, local slab), info."""
+        st = self.cg_begin(B, x0)
+        self.cg_steps(st, tol, maxiter)
+        kit = st['kit']
+        return st['x'], {'kit': kit, 'norm_res': st['norm_res'] if kit > 0 else 0,
+                         'norm_res_log': np.array(st['hist'])}

@@ -204,6 +204,8 @@ cases = [((6, 5), (1.0, 2.0), 0, (0, 0, 0, 1, 0, 0)), ((5, 5), (1.0, 1.0), 1, (0
          ((32, 32, 1024), (1, 1, 2), 1, (0, 1, -1, 1, 0, 0)), ((2048, 16, 16), (1, 1, 1), 0, (0, 1, 0, -1, 0, 0)),
          ((512, 512), (1, 1), 1, (0, 0, 1, -1, 0, 0)), ((1024, 32), (1, 1), 0, (0, 0, 0, 1, 0, 0)),
          ((32, 16), (1, 1), 1, (0, 0, 1, -1, 0, 0)),
+         ((16, 32, 512), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((32, 512), (1, 2), 0, (0, 0, 0, 1, 0, 0)),
+         ((512, 8, 512), (1, 1, 1), 0, (0, 0, 0, 1, 0, 0)),
          # run-time-length kernels (odd / mixed radices), incl. an axis that falls back
          ((15, 15, 15), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)), ((45, 35, 63), (1, 2, 1), 0, (0, 1, 0, -1, 0, 0)),
          ((255, 15, 51), (1, 1, 1), 1, (0, 1, -1, 1, 0, 0)), ((6, 10, 12), (1, 1, 1), 1, (0, 0, 1, -1, 0, 0)),
@@ -274,7 +276,7 @@ for N, Y, kind, coef in cases:
             # same iteration count; the iterates of an ill-conditioned random problem agree to ~cond * eps
             report('cg solution', np.abs(xs.cpu().numpy()-xx).max()/max(np.abs(xx).max(), 1e-300), 1e-6)
             m = min(kit, kk.value)+1
-            report('cg residual history', np.max(np.abs(np.array(hh[:m])-np.array(hist[:m]))/hist[0]), 1e-9)
+            report('cg residual history', np.max(np.abs(np.array(hh[:m])-np.array(hist[:m]))/hist[0]), 1e-8)  # the pytest bar for residual histories (tests/test_gpu_reference_suite.py)
         lib.fh_ga_destroy(op)
         lib.fh_plan_destroy(p)
 

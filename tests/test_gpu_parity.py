@@ -323,3 +323,74 @@ def test_full_size_properties(n):
         A, Afun = harness.build_operator(I6*2.0, G1h+G1s, N)
         ref = O.GA(I6*2.0, sum(O.proj_elasticity(N, np.ones(3))[1:3]), N)(u.val)
         assert np.abs(Afun(u).val-ref).max() < 1e-12*np.abs(ref).max()
+
+
+@pytest.mark.parametrize('N', [(512, 8, 16), (8, 512, 16), (8, 16, 512), (512, 512)])
+@pytest.mark.parametrize('physics', ['elasticity', 'scalar'])
+def test_axis_length_512_against_the_oracle(N, physics):
+    """the register-resident three-pass kernels (csrc/fh_reg3.cuh: S1, S2/S4, S3, S5 at axis length 512, the
+    BASELINE config-4 grid size), one axis at a time: operator application vs the oracle 1e-12 relative, CG
+    iteration counts equal, solution 1e-9"""
+    from ffthompy_b200.tensors import Tensor
+    from ffthompy_b200.general.solver import linear_solver
+    d = len(N)
+    Na = np.array(N)
+    if physics == 'elasticity':
+        D = d*(d+1)//2
+        G = harness.green_for('elasticity', 'GaNi', N, np.ones(d), 'primal')[0]
+        Go = O.proj_elasticity(N, np.ones(d))
+        Go = Go[1]+Go[2]
+        Cm, Ci = (O.elastic_mandel(1, 1), O.elastic_mandel(10, 5)) if d == 3 else (np.eye(3)*2., np.eye(3)*9.+1.)
+    else:
+        D = d
+        G = harness.green_for('scalar', 'GaNi', N, np.ones(d), 'primal')[0]
+        Go = O.proj_scalar(N, np.ones(d))[1]
+        Cm, Ci = np.eye(d), 11.*np.eye(d)
+    rng = np.random.default_rng(11)
+    ph = rng.random(N) < 0.3
+    Aval = np.einsum('ij,...->ij...', Cm, 1.-ph)+np.einsum('ij,...->ij...', Ci, 1.*ph)
+    A, Afun = harness.build_operator(Aval, G, Na)
+    Afo = O.GA(Aval, Go, N)
+    u = rng.standard_normal((D,)+N)
+    ref = Afo(u)
+    got = Afun(Tensor(name='u', val=u, order=1, N=Na)).val
+    assert np.abs(got-ref).max() < 1e-12*np.abs(ref).max()
+    E = np.zeros((D,)+N)
+    E[0] = 1.
+    xo, io = O.cg(Afo, Afo(-E), np.zeros_like(E), 1e-6, 1000, N)
+    EN = Tensor(name='EN', N=Na, shape=(D,), Fourier=False)
+    EN.set_mean(np.eye(D)[0])
+    X, info = linear_solver(solver='CG', Afun=Afun, B=Afun(-EN), x0=EN.zeros_like(), par={'tol': 1e-6, 'maxiter': 1000},
+                            callback=None)
+    assert info['kit'] == io['kit']
+    assert np.abs(X.val-xo).max() < 1e-9
+
+
+def test_deferred_x_update_is_bitwise_the_plain_update():
+    """fh_cg_steps applies x += alpha p inside the next S1 (one field read less per iteration); FH_XDEFER=0
+    keeps it in the update kernel.  Same expressions in the same order: solutions must be bit-identical."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import hashlib, numpy as np
+import ffthom_oracle as O, harness
+from ffthompy_b200 import device
+device.init(0)
+out = []
+for N in [(64, 64, 64), (30, 20, 15), (8, 16, 512)]:
+    G = harness.green_for('elasticity', 'GaNi', N, np.ones(3), 'primal')[0]
+    Aval, _ = O.two_phase(N, 7, 0.3, O.elastic_mandel(1, 1), O.elastic_mandel(10, 5))
+    A, Afun, sols, infos = harness.solve_loads(Aval, G, np.array(N), 1e-7)
+    out.append(hashlib.sha256(np.ascontiguousarray(sols[1].val).tobytes()).hexdigest()+':%d' % infos[1]['kit'])
+print('HASH', ' '.join(out))
+'''
+    here = os.path.dirname(os.path.abspath(harness.__file__))
+    root = os.path.dirname(here)
+    res = {}
+    for flag in ('0', '1'):
+        env = dict(os.environ, FH_XDEFER=flag, PYTHONPATH=os.pathsep.join([root, os.path.join(root, 'oracle'), here]))
+        r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:]+r.stderr[-1500:]
+        res[flag] = [l for l in r.stdout.splitlines() if l.startswith('HASH')][0]
+    assert res['0'] == res['1'], res
