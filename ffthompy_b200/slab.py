@@ -185,7 +185,9 @@ class SlabGA(object):
                 import torch.distributed._symmetric_memory as symm_mem
                 xb = symm_mem.empty(4*nel, dtype=torch.float64, device=dev.device())
                 xb.zero_()
+                torch.cuda.synchronize()   # the zero fill must not overtake a peer's first push into this buffer
                 self.xsymm = symm_mem.rendezvous(xb, group if group is not None else dist.group.WORLD)
+                dist.barrier(group=group)
                 cview = lambda t: torch.view_as_complex(t.reshape(-1, 2))
                 bufA, bufB = cview(xb[:2*nel]), cview(xb[2*nel:])
                 self._xb = xb
