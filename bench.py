@@ -375,7 +375,7 @@ def run_slab(args):
     dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from ffthompy_b200 import device as dev
     import ffthompy_b200.projections as proj
-    from ffthompy_b200.slab import SlabGA, SlabLayout
+    from ffthompy_b200.slab import SlabGA, SlabLayout, best_exchange
     dev.init(local)
     n = args.slab_n
     N = (n, n, n)
@@ -397,7 +397,11 @@ def run_slab(args):
     Ad = make_A()
     _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3), NyqNul=True, tensor=True)
     G = G1h+G1s
-    op = SlabGA(Ad, G, N, exchange=args.exchange)
+    exchange, tuned = args.exchange, None
+    if exchange is None:
+        # set-up, untimed: the faster of the two NVLink exchange schemes for this grid and rank count
+        exchange, tuned = best_exchange(Ad, G, N)
+    op = SlabGA(Ad, G, N, exchange=exchange)
     shape = (D, lay.n0l, n, n)
     E = dev.zeros(shape)
     E[0] = -1.
@@ -495,7 +499,7 @@ def run_slab(args):
         t0 = time.perf_counter()
         A2 = A_host.to(dev.device(), non_blocking=True)
         _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3), NyqNul=True, tensor=True)
-        op2 = SlabGA(A2, G1h+G1s, N, exchange=args.exchange)
+        op2 = SlabGA(A2, G1h+G1s, N, exchange=exchange)
         E2 = dev.zeros(shape)
         E2[0] = -1.
         X, info = op2.cg(op2.apply(E2), dev.zeros(shape), tol=1e-6, maxiter=1000)
@@ -518,6 +522,7 @@ def run_slab(args):
                 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
                 'config': workload_config(n, world, 'gpu', slab='%s (chunks %d)' % (mode, nchunk)),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_all, 'roofline': roofline,
+                'exchange_autotune_ms_per_apply': tuned,
                 'note': 'strong scaling over N = 2, 4, 8 at the fixed 512^3 grid; the N = 1 line is the 256^3 '
                         'single-GPU workload (BASELINE config 3). value is size-normalised (voxel-DOF/s).'}
         print(json.dumps(line), flush=True)

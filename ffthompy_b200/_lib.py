@@ -81,6 +81,10 @@ _SIGNATURES = {
     'fh_ga_slab_stage': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'fh_cgd_init': (c_int, [c_vp, c_vp, c_vp]),
     'fh_cgd_update': (c_int, [c_vp, c_vp, c_vp]),
+    'fh_ga_set_xacc': (c_int, [c_vp, c_vp]),
+    'fh_ga_can_defer_x': (c_int, [c_vp]),
+    'fh_cgd_update_r': (c_int, [c_vp, c_vp]),
+    'fh_cgd_xflush': (c_int, [c_vp, c_vp, c_vp]),
     'fh_cgd_local_sum': (c_int, [c_vp, c_vp]),
     'fh_cgd_scal': (c_int, [c_vp, c_vp, c_int, p_dbl]),
     'fh_cg_xr_update': (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_dbl, p_dbl]),

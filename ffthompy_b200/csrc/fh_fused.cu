@@ -1369,6 +1369,7 @@ static int launch_c2c_map_NT(const cplx* tw, const cplx* in, cplx* out, const Li
 }
 static int launch_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
                           int64_t panels, int pitch, bool inv) {
+    if (use_reg3() && fh_reg3_map_len(N) && pitch % 8 == 0) return fh_reg3_c2c_map(N, tw, in, out, mi, mo, panels, pitch, inv);
     switch (N) {
         case 16: return launch_c2c_map_NT<16, 8>(tw, in, out, mi, mo, panels, pitch, inv);
         case 32: return launch_c2c_map_NT<32, 8>(tw, in, out, mi, mo, panels, pitch, inv);
@@ -1445,6 +1446,9 @@ static int launch_mid_map_NT(fh_ga* op) {
     const size_t smem = (size_t)(N + N / 16) * D * T * sizeof(cplx);
     if (smem > (size_t)fh_max_smem_optin())
         return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: N0=%d D=%d does not fit shared memory", N, D);
+    if (!(op->sd_peer && op->sd_world > 1) && use_reg3() && fh_reg3_map_len(N) && inner % 8 == 0)
+        return fh_reg3_mid_green_map(N, KIND, op->sd_peer ? op->spec : op->sd_bufB, p->ax[0].tw, op->g, inner, p->nh,
+                                     op->pitch, op->sd_off0, op->sd_cs0);
     // rows in peer memory: move 128-byte (FH_XSEG=256: 256-byte) segments through a CTA cluster
     if (op->sd_peer && op->sd_world > 1) {
         static const int seg = env_int("FH_XSEG", 128);
@@ -1659,6 +1663,39 @@ extern "C" int fh_cgd_update(fh_ga* op, double* x, double* vecs) {
         k_cg_update1<<<g, GA_NT, 0, fh_stream()>>>(n, x, r, p, Ap, op->scal, op->part);
     FH_LAUNCH_CHECK();
     op->last_npart = (int)g;
+    return FH_OK;
+}
+// Deferred x update for the distributed loop (same scheme as fh_cg_steps): fh_ga_set_xacc(op, x) makes the next S1
+// launches with a p update also apply x += alpha p (alpha = the device scalar of the previous iteration);
+// fh_cgd_update_r is the update without x; fh_cgd_xflush applies the pending x += alpha p after the last iteration.
+extern "C" int fh_ga_set_xacc(fh_ga* op, double* x) {
+    FH_REQUIRE(op, "fh_ga_set_xacc: null operator");
+    FH_REQUIRE(x == NULL || op->fast_last || op->rt_ok[op->plan->dim - 1],
+               "fh_ga_set_xacc: this operator's S1 path does not carry the p update");
+    op->xacc = x;
+    return FH_OK;
+}
+extern "C" int fh_ga_can_defer_x(const fh_ga* op) {
+    if (!op) return 0;
+    const int64_t n = (int64_t)op->D * op->nloc;
+    return (n % 2 == 0 && (op->fast_last || op->rt_ok[op->plan->dim - 1]) && env_int("FH_XDEFER", 1)) ? 1 : 0;
+}
+extern "C" int fh_cgd_update_r(fh_ga* op, double* vecs) {
+    FH_REQUIRE(op && vecs, "fh_cgd_update_r: null argument");
+    const int64_t n = (int64_t)op->D * op->nloc;
+    FH_REQUIRE(n % 2 == 0 && ((uintptr_t)vecs & 15) == 0, "fh_cgd_update_r: even, 16-byte aligned fields required");
+    const unsigned g = ga_grid(n / 2 + 1);
+    k_cg_update_r<<<g, GA_NT, 0, fh_stream()>>>(n / 2, (double2*)vecs, (const double2*)(vecs + 2 * n), op->scal, op->part);
+    FH_LAUNCH_CHECK();
+    op->last_npart = (int)g;
+    return FH_OK;
+}
+extern "C" int fh_cgd_xflush(fh_ga* op, double* x, const double* vecs) {
+    FH_REQUIRE(op && x && vecs, "fh_cgd_xflush: null argument");
+    const int64_t n = (int64_t)op->D * op->nloc;
+    FH_REQUIRE(n % 2 == 0 && (((uintptr_t)x | (uintptr_t)vecs) & 15) == 0, "fh_cgd_xflush: even, 16-byte aligned fields required");
+    k_cg_xflush<<<ga_grid(n / 2 + 1), GA_NT, 0, fh_stream()>>>(n / 2, (double2*)x, (const double2*)(vecs + n), op->scal);
+    FH_LAUNCH_CHECK();
     return FH_OK;
 }
 // sum_dev[0] = this rank's sum of the partial sums left by the last S5 / init / update launch

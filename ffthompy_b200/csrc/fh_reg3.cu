@@ -72,13 +72,15 @@ int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
 }
 
 template <int N, int T, int KIND, int DIM>
-static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch) {
+static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
+                  const int64_t* rowoff = nullptr, int64_t cstride = 0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int NT = 768;
     const size_t smem = (size_t)D * (N + N / 8) * T * sizeof(cplx);
     int rc;
     if ((rc = reg3_smem_attr(k_mid_green_reg3<N, T, KIND, DIM, NT>, smem))) return rc;
-    k_mid_green_reg3<N, T, KIND, DIM, NT><<<(unsigned)(inner / T), NT, smem, fh_stream()>>>(data, tw, g, inner, nh, pitch);
+    k_mid_green_reg3<N, T, KIND, DIM, NT><<<(unsigned)(inner / T), NT, smem, fh_stream()>>>(
+        data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -93,4 +95,45 @@ int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, cons
                           : mid_KD<512, 4, FH_GREEN_SCALAR, 2>(data, tw, g, inner, nh, pitch);
     return (dim == 3) ? mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch)
                       : mid_KD<512, 4, FH_GREEN_ELASTIC, 2>(data, tw, g, inner, nh, pitch);
+}
+
+// slab-exchange layout (fh_ga_slab_direct): rows through rowoff[], component stride cstride; 3-D only
+bool fh_reg3_map_len(int n) {
+    static const int m256 = reg3_env("FH_MAP256_REG3", 0);
+    return n == 512 || (n == 256 && m256);
+}
+int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                          int pitch, const int64_t* rowoff, int64_t cstride) {
+    if (N == 512 && inner % 4 == 0) {
+        if (kind == FH_GREEN_SCALAR) return mid_KD<512, 4, FH_GREEN_SCALAR, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
+        return mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
+    }
+    if (N == 256 && inner % 8 == 0 && kind == FH_GREEN_ELASTIC)
+        return mid_KD<256, 8, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass axis-0 exchange kernel for N0=%d", N);
+}
+template <int N, int T>
+static int c2c_map_NT(const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo, int64_t panels,
+                      int pitch, bool inv) {
+    const size_t smem = (size_t)N * T * sizeof(cplx);
+    const int ntile = pitch / T;
+    const unsigned nblk = (unsigned)(panels * ntile);
+    const int nt = T * Reg3Cfg<N>::TPL;
+    int rc;
+    if (inv) {
+        if ((rc = reg3_smem_attr(k_c2c_reg3_map<N, T, true>, smem))) return rc;
+        k_c2c_reg3_map<N, T, true><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+    } else {
+        if ((rc = reg3_smem_attr(k_c2c_reg3_map<N, T, false>, smem))) return rc;
+        k_c2c_reg3_map<N, T, false><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+    }
+    FH_LAUNCH_CHECK();
+    return FH_OK;
+}
+int fh_reg3_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
+                    int64_t panels, int pitch, bool inv) {
+    if (pitch % 8) return fh_set_error(FH_ERR_UNSUPPORTED, "three-pass exchange kernel: pitch %d", pitch);
+    if (N == 512) return c2c_map_NT<512, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+    if (N == 256) return c2c_map_NT<256, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+    return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass exchange kernel for N1=%d", N);
 }

@@ -269,10 +269,12 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
 // data [D][N][inner]; one CTA owns T consecutive inner positions of all D components; the tile sits in
 // shared memory as [D][N + N/8][T] complex.  NT threads walk the D*T*(N/R) butterflies of each pass
 // (pass 1 straight from global memory, inverse pass 1 straight back).
+// Addressing: element (c, row, ii) at  c * cstride + (rowoff ? rowoff[row] : row * inner) + ii  — the natural
+// [D][N][inner] array (rowoff = NULL, cstride = N * inner) or a slab-exchange buffer (fh_ga_slab_direct).
 template <int N, int T, int KIND, int DIM, int NT>
 __global__ void __launch_bounds__(NT, 1)
     k_mid_green_reg3(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
-                     int pitch) {
+                     int pitch, const int64_t* __restrict__ rowoff, int64_t cstride) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
     constexpr int B1 = Reg3Cfg<N>::B1, B2 = Reg3Cfg<N>::B2, B3 = Reg3Cfg<N>::B3;
@@ -283,10 +285,10 @@ __global__ void __launch_bounds__(NT, 1)
     // F1: global -> registers -> smem
     for (int w = threadIdx.x; w < D * B1 * T; w += NT) {
         const int t = w % T, u = (w / T) % B1, c = w / (T * B1);
-        const cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+        const cplx* gp = data + (int64_t)c * cstride + i0 + t;
         cplx v[R1];
 #pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = gp[(int64_t)(u + r * M) * inner];
+        for (int r = 0; r < R1; ++r) v[r] = gp[rowoff ? rowoff[u + r * M] : (int64_t)(u + r * M) * inner];
         Bfly<R1, false>::run(v);
 #pragma unroll
         for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, false));
@@ -396,8 +398,59 @@ __global__ void __launch_bounds__(NT, 1)
 #pragma unroll
         for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, true));
         Bfly<R1, true>::run(v);
-        cplx* gp = data + (int64_t)c * N * inner + i0 + t;
+        cplx* gp = data + (int64_t)c * cstride + i0 + t;
 #pragma unroll
-        for (int r = 0; r < R1; ++r) gp[(int64_t)(u + r * M) * inner] = v[r];
+        for (int r = 0; r < R1; ++r) gp[rowoff ? rowoff[u + r * M] : (int64_t)(u + r * M) * inner] = v[r];
+    }
+}
+
+// ------------------------------------------------------------------ S2 / S4 between the natural x-slab spectrum and a
+// slab-exchange buffer (out of place, LineMap addressing of fh_fast.cuh): k_c2c_reg3 with mapped rows
+template <int N, int T, bool INV>
+__global__ void __launch_bounds__(T* Reg3Cfg<N>::TPL) k_c2c_reg3_map(const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                                      const cplx* __restrict__ tw, LineMap mi, LineMap mo,
+                                                                      int ntile) {
+    constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
+    constexpr int M = N / R1;
+    extern __shared__ __align__(16) unsigned char fh_smem_raw[];
+    cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [N][T]
+    const int t = threadIdx.x % T, u = threadIdx.x / T;
+    const int64_t o = blockIdx.x / ntile;
+    const int tile = blockIdx.x - (int)(o * ntile);
+    const int64_t bi = linemap_base(mi, o) + (int64_t)tile * T + t;
+    const int64_t bo = linemap_base(mo, o) + (int64_t)tile * T + t;
+    if (u < Reg3Cfg<N>::B1) {
+        cplx v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = in[bi + linemap_row(mi, u + r * M)];
+        Bfly<R1, INV>::run(v);
+#pragma unroll
+        for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, INV));
+#pragma unroll
+        for (int q = 0; q < R1; ++q) smc[(q * M + u) * T + t] = v[q];
+    }
+    __syncthreads();
+    if (u < Reg3Cfg<N>::B2) {
+        const int q = u / R3, jp = u - q * R3;
+        cplx* sp = smc + (q * M + jp) * T + t;
+        cplx v[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = sp[r * R3 * T];
+        Bfly<R2, INV>::run(v);
+#pragma unroll
+        for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, INV));
+#pragma unroll
+        for (int q2 = 0; q2 < R2; ++q2) sp[q2 * R3 * T] = v[q2];
+    }
+    __syncthreads();
+    if (u < Reg3Cfg<N>::B3) {
+        const int q = u % R1, q2 = u / R1;
+        const cplx* sp = smc + (q * M + q2 * R3) * T + t;
+        cplx v[R3];
+#pragma unroll
+        for (int jp = 0; jp < R3; ++jp) v[jp] = sp[jp * T];
+        Bfly<R3, INV>::run(v);
+#pragma unroll
+        for (int k = 0; k < R3; ++k) out[bo + linemap_row(mo, u + R1 * R2 * k)] = v[k];
     }
 }

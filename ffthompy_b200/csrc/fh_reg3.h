@@ -37,3 +37,11 @@ int fh_reg3_fwd_last(int N, int D, int trw, const Reg3LastArgs& a);
 int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a);
 int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
                       int pitch);
+
+// slab-exchange layouts (LineMap of fh_fast.cuh; rowoff / cstride of fh_ga_slab_direct)
+struct LineMap;
+bool fh_reg3_map_len(int n);
+int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                          int pitch, const int64_t* rowoff, int64_t cstride);
+int fh_reg3_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
+                    int64_t panels, int pitch, bool inv);

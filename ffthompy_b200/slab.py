@@ -107,6 +107,48 @@ def direct_offsets(layout, D, P, nchunk):
     return off1, off0, n0c*inner, inner, n0c*inner, G*D*n0c*inner
 
 
+def best_exchange(A_local, G, N, group=None, modes=('peer', 'p2p'), reps=3):
+    """Measure, don't guess: build the operator with each exchange mode in `modes`, time `reps` applications on
+    the device (max over ranks, so every rank takes the same decision) and return (name, {name: ms}).  Modes
+    whose kernels or memory mappings are not available here are skipped; which one wins depends on grid size
+    and rank count (2 x B200: 'peer' at 256^3, 'p2p' at 512^3)."""
+    import torch
+    import torch.distributed as dist
+    from . import device as dev
+    times = {}
+    for m in modes:
+        ok = torch.ones(1, device=dev.device())
+        op = None
+        try:
+            op = SlabGA(A_local, G, N, group=group, exchange=m)
+        except Exception:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+        if ok.item() == 0:
+            del op
+            continue
+        x = dev.zeros(tuple(A_local.shape[1:]))
+        x.normal_()
+        y = dev.zeros(tuple(A_local.shape[1:]))
+        op.apply(x, y)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            op.apply(x, y)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)/reps], dtype=torch.float64, device=dev.device())
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        times[m] = float(t.item())
+        del op, x, y
+        torch.cuda.empty_cache()
+    if not times:
+        return None, times
+    return min(times, key=lambda k: times[k]), times
+
+
 class SlabGA(object):
     """y = F^-1 G^ F (A x) on slab-decomposed fields, and the CG loop of general/solver.py:80-139
     over it.  `A_local`: device tensor [D][D][n0l][N1][N2]; `G`: lazy GreenTensor on the GLOBAL grid.
@@ -375,14 +417,31 @@ class SlabGA(object):
         Returns the number of iterations done."""
         L, lib, dev = self.L, self.dev.lib(), self.dev
         done = 0
+        # deferred x update (as in fh_cg_steps): x += alpha p of iteration k is applied by S1 of iteration k+1,
+        # which has p in registers anyway (one field read less per iteration), and flushed before returning
+        defer = bool(lib.fh_ga_can_defer_x(self.handle))
+        pending = False
         while st['norm_res'] > tol and done < nsteps:
             done += 1
-            self.apply(st['p'], st['Ap'], r=st['r'], pupdate=st['have_beta'])  # p = r + beta p folded into S1
+            if pending:
+                L.check(lib.fh_ga_set_xacc(self.handle, dev.ptr(st['x'])))
+            try:
+                self.apply(st['p'], st['Ap'], r=st['r'], pupdate=st['have_beta'])  # p = r + beta p folded into S1
+            finally:
+                if pending:
+                    L.check(lib.fh_ga_set_xacc(self.handle, None))
+            pending = False
             self._global_scalar(1, False)
-            L.check(lib.fh_cgd_update(self.handle, dev.ptr(st['x']), dev.ptr(st['vecs'])))
+            if defer:
+                L.check(lib.fh_cgd_update_r(self.handle, dev.ptr(st['vecs'])))
+                pending = True
+            else:
+                L.check(lib.fh_cgd_update(self.handle, dev.ptr(st['x']), dev.ptr(st['vecs'])))
             st['norm_res'] = self._global_scalar(2, True)
             st['have_beta'] = 1
             st['hist'].append(st['norm_res'])
+        if pending:
+            L.check(lib.fh_cgd_xflush(self.handle, dev.ptr(st['x']), dev.ptr(st['vecs'])))
         st['kit'] += done
         return done
 

@@ -153,6 +153,14 @@ int fh_ga_slab_stage(fh_ga* op, int stage, int chunk, double* p, const double* r
  * ranks, fh_cgd_scal turns the global sum into rr/norm (mode 0), alpha (1) or beta/rr/norm (2). */
 int fh_cgd_init(fh_ga* op, const double* B, double* vecs);
 int fh_cgd_update(fh_ga* op, double* x, double* vecs);
+/* deferred x update (what fh_cg_steps does internally): with fh_ga_set_xacc(op, x) the next S1 launches that
+ * carry the p update also apply x += alpha p of the previous iteration (solver.py:127) while p is in registers;
+ * fh_cgd_update_r is then the update without x (r -= alpha Ap, partial <r,r>), fh_cgd_xflush applies the
+ * pending x += alpha p after the last iteration.  fh_ga_can_defer_x: 1 if this operator's S1 path supports it. */
+int fh_ga_set_xacc(fh_ga* op, double* x);
+int fh_ga_can_defer_x(const fh_ga* op);
+int fh_cgd_update_r(fh_ga* op, double* vecs);
+int fh_cgd_xflush(fh_ga* op, double* x, const double* vecs);
 int fh_cgd_local_sum(fh_ga* op, double* sum_dev);
 int fh_cgd_scal(fh_ga* op, const double* sum_dev, int mode, double* norm_host);
 /* this rank's sum of x*y left on the device by the last fh_ga_stage(op, 5, x, y) */
