@@ -280,7 +280,7 @@ def run_ours(args):
         tag = {1: 'k_fwd_last_fast', 2: 'k_c2c_fast<256, 8, 0>', 3: 'k_mid_green_pipe', 4: 'k_c2c_fast<256, 8, 1>',
                5: 'k_inv_last_fast'}[dom]
         if n == 256:
-            traffic = [v for k, v in tj.items() if k.startswith(tag)][0]
+            traffic = [v for k, v in tj.items() if tag in k][0]
     except Exception:
         traffic = None
     achieved = alg[dom]/(stage_ms[dom]*1e-3)/1e9
