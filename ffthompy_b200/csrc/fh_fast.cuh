@@ -349,8 +349,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
 // ------------------------------------------------------------------ last axis, inverse, fused with <p, y>
 // y[D][rows][N] = scale * C2R(spec); if pdot != NULL also part[blockIdx.x] = sum over the CTA's
 // voxels of pdot*y  (the p.Ap of CG, solver.py:126).
-template <int N, int D, int TRW>
-__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+template <int N, int D, int TRW, int MINB = 1>
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL, MINB)
     k_inv_last_fast(const cplx* __restrict__ spec, double* __restrict__ y, const double* __restrict__ pdot,
                     double* __restrict__ part, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
                     double scale) {

@@ -52,6 +52,7 @@ struct fh_ga {
     bool rt_ok[3];   // run-time-length in-place kernels usable on axis a (any N = up to 3 supported radices)
     RtPlan rt[3];
     int mid_T, trw, mid_pipe;
+    int trw_s1;          // rows per CTA of S1 when it differs from trw (0: same)
     int chunk_cols;      // L2 blocking of S2-S3-S4: columns of the spectrum rows per chunk (0 = off)
     int cur_col0, cur_ncols;  // chunk the next S3 launch works on (0,0 = whole rows)
     // device scalars / partial sums of the Krylov loops
@@ -467,6 +468,18 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     int rc;
     if ((rc = smem_attr(k_inv_last_fast<N, D, TRW>, smem))) return rc;
     if (pdot && rr_.pb + nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
+    if constexpr (N == 256 && D == 6 && TRW == 4) {
+        static const int lb4 = env_int("FH_S5_LB4", 0);  // experiment: four CTAs per SM (registers capped at 85)
+        if (lb4) {
+            if ((rc = smem_attr(k_inv_last_fast<N, D, TRW, 4>, smem))) return rc;
+            k_inv_last_fast<N, D, TRW, 4><<<nblk, nt, smem, fh_stream()>>>(
+                op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
+                op->nrows, pl->nh, op->pitch, 1.0 / (double)pl->nreal);
+            FH_LAUNCH_CHECK();
+            if (npart) *npart = (int)(rr_.pb + nblk);
+            return FH_OK;
+        }
+    }
     k_inv_last_fast<N, D, TRW><<<nblk, nt, smem, fh_stream()>>>(op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
                                                                 op->nrows, pl->nh, op->pitch,
                                                                 1.0 / (double)pl->nreal);
@@ -775,10 +788,19 @@ static bool reg3_last_ok(const fh_ga* op) {
     return use_reg3() && fh_reg3_last_len(nl) && (op->D == 6 || op->D == 3 || op->D == 2) &&
            op->trw == ((op->D == 6) ? 2 : 4);
 }
+static int launch_fwd_last_two_pass(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
+    FH_LAST_DISPATCH(launch_fwd_last_NT, op, p, r, pupdate, withA);
+}
 static int launch_fwd_last_fast(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
     if (reg3_last_ok(op)) return launch_fwd_last_reg3(op, p, r, pupdate, withA);
     if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_fwd_last_gen3(op, p, r, pupdate, withA);
-    FH_LAST_DISPATCH(launch_fwd_last_NT, op, p, r, pupdate, withA);
+    // S1 and S5 choose their rows-per-CTA independently (the spectrum layout does not depend on it): S1 is a
+    // streaming kernel that gains from more, smaller CTAs per SM (2 rows), S5 runs best with 4
+    const int keep = op->trw;
+    if (op->trw_s1) op->trw = op->trw_s1;
+    const int rc = launch_fwd_last_two_pass(op, p, r, pupdate, withA);
+    op->trw = keep;
+    return rc;
 }
 static int launch_inv_last_fast(fh_ga* op, double* y, const double* pdot, int* npart) {
     if (reg3_last_ok(op)) return launch_inv_last_reg3(op, y, pdot, npart);
@@ -953,6 +975,7 @@ static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, i
     if (D == 6 && !fh_gen3_len(plan->N[d - 1]) && env_int("FH_TRW", 4) == 2) op->trw = 2;
     auto pow2fast = [](int n) { return fh_fast_len(n) || fh_gen3_len(n); };
     op->fast_last = use_fast && pow2fast(plan->N[d - 1]) && (op->nrows % op->trw == 0);
+    op->trw_s1 = (D == 6 && op->trw == 4 && !fh_gen3_len(plan->N[d - 1]) && env_int("FH_TRW_S1", 2) == 2) ? 2 : 0;
     op->fast_mid1 = use_fast && d == 3 && pow2fast(plan->N[1]);
     op->fast_mid0 = use_fast && pow2fast(plan->N[0]) && (((int64_t)op->n1l * op->pitch) % 4 == 0);
     const int use_rt = env_int("FH_RT", 7);

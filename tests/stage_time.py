@@ -52,4 +52,12 @@ torch.cuda.synchronize(); t0 = time.perf_counter()
 L.check(lib.fh_cg_steps(op, ptr(xs), ptr(vecs), 0.0, 20, C.byref(done), C.byref(nr), None))
 torch.cuda.synchronize(); t = (time.perf_counter()-t0)/20*1e3
 out.append('CG %.3f ms/it %.1f it/s' % (t, 1e3/t))
+if lib.fh_ga_can_defer_x(op):
+    r_, p_ = vecs[:D*nreal], vecs[D*nreal:2*D*nreal]
+    L.check(lib.fh_ga_set_xacc(op, ptr(xs)))
+    t = timeit(lambda: L.check(lib.fh_ga_slab_stage(op, 1, 0, ptr(p_), ptr(r_), 1, ptr(y))))
+    L.check(lib.fh_ga_set_xacc(op, None))
+    out.append('S1cg %.3f ms %.0f GB/s' % (t, (5*F+CA+Fs)/t/1e6))
+    t = timeit(lambda: L.check(lib.fh_cgd_update_r(op, ptr(vecs))))
+    out.append('U %.3f ms %.0f GB/s' % (t, 3*F/t/1e6))
 print(' | '.join(out))
