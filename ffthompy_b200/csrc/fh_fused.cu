@@ -468,18 +468,6 @@ static int launch_inv_last_NT(fh_ga* op, double* y, const double* pdot, int* npa
     int rc;
     if ((rc = smem_attr(k_inv_last_fast<N, D, TRW>, smem))) return rc;
     if (pdot && rr_.pb + nblk > GA_MAXPART) return fh_set_error(FH_ERR_UNSUPPORTED, "too many partial sums (%u)", nblk);
-    if constexpr (N == 256 && D == 6 && TRW == 4) {
-        static const int lb4 = env_int("FH_S5_LB4", 0);  // experiment: four CTAs per SM (registers capped at 85)
-        if (lb4) {
-            if ((rc = smem_attr(k_inv_last_fast<N, D, TRW, 4>, smem))) return rc;
-            k_inv_last_fast<N, D, TRW, 4><<<nblk, nt, smem, fh_stream()>>>(
-                op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
-                op->nrows, pl->nh, op->pitch, 1.0 / (double)pl->nreal);
-            FH_LAUNCH_CHECK();
-            if (npart) *npart = (int)(rr_.pb + nblk);
-            return FH_OK;
-        }
-    }
     k_inv_last_fast<N, D, TRW><<<nblk, nt, smem, fh_stream()>>>(op->spec + rr_.so, y + rr_.ro, pdot ? pdot + rr_.ro : nullptr, op->part + rr_.pb, pl->ax[pl->dim - 1].tw,
                                                                 op->nrows, pl->nh, op->pitch,
                                                                 1.0 / (double)pl->nreal);
@@ -794,10 +782,11 @@ static int launch_fwd_last_two_pass(fh_ga* op, double* p, const double* r, int p
 static int launch_fwd_last_fast(fh_ga* op, double* p, const double* r, int pupdate, bool withA) {
     if (reg3_last_ok(op)) return launch_fwd_last_reg3(op, p, r, pupdate, withA);
     if (fh_gen3_len(op->plan->N[op->plan->dim - 1])) return launch_fwd_last_gen3(op, p, r, pupdate, withA);
-    // S1 and S5 choose their rows-per-CTA independently (the spectrum layout does not depend on it): S1 is a
-    // streaming kernel that gains from more, smaller CTAs per SM (2 rows), S5 runs best with 4
+    // S1 and S5 choose their rows-per-CTA independently (the spectrum layout does not depend on it).  Measured at
+    // 256^3: the plain S1 (operator application) runs best with 2 rows per CTA (0.419 vs 0.449 ms), its CG form
+    // (x and p updates folded in) and S5 with 4 (0.947 vs 0.963 ms)
     const int keep = op->trw;
-    if (op->trw_s1) op->trw = op->trw_s1;
+    if (op->trw_s1 && !pupdate) op->trw = op->trw_s1;
     const int rc = launch_fwd_last_two_pass(op, p, r, pupdate, withA);
     op->trw = keep;
     return rc;
