@@ -140,9 +140,10 @@ def run_reference(args):
     line = {
         'impl': 'reference', 'metric': 'cg_voxel_dof_per_s', 'value': val, 'unit': 'voxel-DOF/s',
         'cg_iterations_per_s': 1./t_iter, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t_iter*1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'ms_per_step': t_iter*1e3, 'higher_is_better': True,
+        'scaling': 'strong' if (args.gpus > 1 and args.mode == 'slab') else 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
-        'config': workload_config(args.n, 1, 'cpu'),
+        'config': ref_config(args),
         'cpu_baseline': {'value': val, 'unit': 'voxel-DOF/s', 'cores': 1, 'kind': 'port',
                          'sample': 'oracle CG iterations (NumPy rfftn/einsum, materialised G^) at %d^3 of the same '
                                    'generator; numpy.fft and einsum are single-threaded (host has %d cores)'
@@ -167,6 +168,15 @@ def workload_config(n, ngpu, where, slab=None):
             'grid': [n, n, n], 'D': 6, 'step': 'one CG iteration',
             'l2': 'working set per iteration (%.1f GB) exceeds the 126 MB L2; no flush needed' % (51*8*n**3/1e9),
             'parallelism': 'replicas x%d (independent solves, no collective)' % ngpu if ngpu > 1 else 'single GPU'}
+
+
+def ref_config(args):
+    """the reference arm reports the config of the GPU arm at the same N (256^3 single GPU; the 512^3 solve for N > 1)"""
+    if args.gpus > 1 and args.mode == 'slab':
+        cfg = workload_config(args.slab_n, args.gpus, 'cpu', slab='n/a')
+        cfg['parallelism'] = 'reference arm: NumPy path on the host cores of rank 0 (no decomposition)'
+        return cfg
+    return workload_config(args.n, 1, 'cpu')
 
 
 # ----------------------------------------------------------------------------- GPU arm
