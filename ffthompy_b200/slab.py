@@ -398,6 +398,46 @@ class SlabGA(object):
         self.exchanged_bytes += 2*self.bufA.numel()*16*(self.layout.world-1)//self.layout.world
         return y
 
+    def profile_apply(self, x, y=None, reps=3):
+        """Where one operator application spends its time on this rank: {phase: ms} from CUDA events on the main
+        stream (max over ranks), for the two NVLink schemes.  p2p: 'fwd' = S1+S2 of all chunks up to the moment
+        every push has landed, 'S3', 'bwd' = pushes back + S4+S5; 'fwd_compute' / 'bwd_compute' are the same
+        stages run back to back without the exchange, so the differences are the exposed (not hidden) transfer
+        time.  peer: the five stages with the two device barriers.  A diagnostic, not used by the solve."""
+        import torch
+        import torch.distributed as dist
+        if y is None:
+            y = self.dev.empty(x.shape)
+        J = self.nchunk
+        marks = {}
+
+        def timed(name, fn):
+            ts = []
+            for _ in range(reps+1):
+                torch.cuda.synchronize()
+                dist.barrier(group=self.group)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn()
+                b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            t = torch.tensor([min(ts[1:])], dtype=torch.float64, device=self.dev.device())
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            marks[name] = float(t.item())
+
+        timed('apply', lambda: self.apply(x, y))
+        if self.mode in ('p2p', 'direct'):
+            timed('fwd_compute', lambda: [self._stage(1, j, x, None, 0, y) for j in range(J)])
+            timed('S3', lambda: self._stage(3, 0, x, None, 0, y))
+            timed('bwd_compute', lambda: [self._stage(4, j, x, None, 0, y) for j in range(J)])
+            marks['exchange_exposed'] = marks['apply']-marks['fwd_compute']-marks['S3']-marks['bwd_compute']
+        else:
+            for st in (1, 2, 3, 4, 5):
+                timed('S%d' % st, lambda st=st: self._stage(st, 0, x, None, 0, y))
+            marks['barriers_and_gaps'] = marks['apply']-sum(marks['S%d' % st] for st in (1, 2, 3, 4, 5))
+        return marks
+
     def last_dot(self):
         """global <x, y> of the most recent apply(x, y): S5 already left this rank's partial sums on the
         device (no extra pass over the fields)"""

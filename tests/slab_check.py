@@ -129,6 +129,14 @@ def main():
                   '%.3e voxel-DOF/s, %.1f%% of the aggregate HBM roofline; NVLink %.2f GB sent per GPU per iteration'
                   % (op.mode, op.nchunk, kind, n, world, per*1e3, 1./per, D*nvox/per,
                      100*rec['hbm_roofline_frac'], nv/1e9), flush=True)
+        if '--profile' in sys.argv and op.mode in ('peer', 'p2p', 'direct'):
+            xp = dev.zeros((D, lay.n0l)+N[1:])
+            xp.normal_()
+            marks = op.profile_apply(xp)
+            if rank == 0:
+                print('profile [ms] (%s, J=%d): ' % (op.mode, op.nchunk)+' | '.join('%s %.3f' % kv for kv in marks.items()),
+                      flush=True)
+            del xp
         if '--stages' in sys.argv and op.mode in ('peer', 'packed'):
             # per-stage device time with every rank inside the same stage (barrier in front of each launch)
             x = dev.zeros((D, lay.n0l)+N[1:])
