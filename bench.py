@@ -11,8 +11,15 @@ N > 1 GPUs (torchrun, one rank per GPU) run ONE slab-decomposed solve of BASELIN
 generator at 512^3, x-planes split over the ranks, FFT transposes over NVLink (ffthompy_b200/slab.py),
 CG scalars by all-reduce; `--mode replicas` runs N independent 256^3 solves instead.
 
-`--impl reference` times the CPU restatement of the reference's NumPy path (oracle/, the reference
-itself cannot travel to the GPU box) on a bounded sample of the same workload.
+`--impl reference` times the reference's own CPU implementation of the path on the host cores: the UNMODIFIED
+reference tree when it is present under baseline/_ref/ (a git-ignored copy made by __graft_entry__.build() where
+/root/reference exists; kind "reference"), else the oracle restatement (oracle/, kind "port") -- on a bounded
+sample (128^3) of the same generator; the line's config.grid is the grid that was actually timed.
+
+Extra keys of the N = 1 line (task 4): `coefficient_modes` (the same CG step with the coefficients
+streamed as a symmetric array and as a full DxD array instead of the 1-byte phase table), `config2_255` (BASELINE
+config 2 shape: 3-D scalar, Ga grid 255^3), `strong_base` (the 512^3 solve on ONE GPU: the strong-scaling base of
+the N > 1 lines, with kit and A_H[0,0] for the 1 <-> N agreement check), `solution` (kit, A_H[0,0] of the timed grid).
 """
 import argparse
 import ctypes as C
@@ -29,7 +36,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SEED = 20240901
-CPU_SAMPLE_N = 96
+CPU_SAMPLE_N = 128          # the CPU path is timed at 128^3 (3.8 s / iteration, 5 GB)
+REF_TREE = os.path.join(ROOT, 'baseline', '_ref')
 
 
 def measured_peaks():
@@ -129,25 +137,109 @@ def cpu_cg_rate(n, iters, warm=1):
     return float(np.mean(times[warm:])), times[warm:]
 
 
+def reference_tree():
+    """the unmodified reference under baseline/_ref (copied there by __graft_entry__.build()), or None"""
+    return REF_TREE if os.path.isdir(os.path.join(REF_TREE, 'ffthompy')) else None
+
+
+def ref_cg_rate(n, iters, warm=1):
+    """seconds per CG iteration of the UNMODIFIED reference (ffthompy Tensor / DFT / Operator from baseline/_ref,
+    SURVEY App. C recipe, even-N projection per App. D.1 built from reference functions only) at n^3"""
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    os.environ['FFTHOMPY_REFERENCE'] = REF_TREE
+    import _refshim
+    _refshim.REFERENCE = REF_TREE
+    _refshim.install()
+    import ffthompy.projections as rproj
+    from ffthompy.tensors import Tensor as RTensor, DFT as RDFT, Operator as ROperator
+    from ffthompy.trigpol import get_Nodd
+    N = np.array([n, n, n])
+    rng = np.random.default_rng(SEED)
+    phase = (rng.random((n, n, n)) < 0.3).astype(float)
+    Cm, Ci = elastic_mandel(1, 1), elastic_mandel(10, 5)
+    A = RTensor(name='A', val=np.einsum('ij,...->ij...', Cm, 1-phase)+np.einsum('ij,...->ij...', Ci, phase),
+                order=2, N=N, multype=21)
+    if n % 2:
+        Gs = rproj.elasticity(N, np.ones(3), NyqNul=True, tensor=True)
+    else:
+        Gs = rproj.elasticity(get_Nodd(N), np.ones(3), NyqNul=False, tensor=True, fft_form=0)[:3]
+        Gs = [G.enlarge(N) for G in Gs]
+        for G in Gs:
+            G.set_fft_form('r')
+            G.val = G.val/np.prod(G.N)
+    G1 = Gs[1]+Gs[2]
+    del Gs
+    Afun = ROperator(name='FiGFA', mat=[[ROperator(name='G', mat=[[RDFT(inverse=True, N=N), G1, RDFT(inverse=False, N=N)]]), A]])
+    EN = RTensor(name='EN', N=N, shape=(6,), Fourier=False)
+    EN.set_mean(np.eye(6)[0])
+    B = Afun(-EN)
+    # the loop body of ffthompy/general/solver.py:123-136 with the reference's own Tensor algebra
+    x = EN.zeros_like()
+    R = B-Afun(x)
+    P = R
+    rr = R*R
+    times = []
+    for it in range(warm+iters):
+        t0 = time.perf_counter()
+        AP = Afun(P)
+        alp = float(rr/(P*AP))
+        x = x+alp*P
+        R = R-alp*AP
+        rrn = R*R
+        P = R+(rrn/rr)*P
+        rr = rrn
+        times.append(time.perf_counter()-t0)
+    return float(np.mean(times[warm:])), times[warm:]
+
+
+def host_ram_gb():
+    try:
+        with open('/proc/meminfo') as f:
+            for line in f:
+                if line.startswith('MemTotal'):
+                    return float(line.split()[1])/1e6
+    except Exception:
+        pass
+    return None
+
+
+def cpu_baseline(iters, warm=1):
+    """(seconds per iteration, cpu_baseline dict) of the CPU path at CPU_SAMPLE_N^3: the reference itself when its tree
+    travelled with the repo, else the oracle port"""
+    n = CPU_SAMPLE_N
+    if reference_tree():
+        t_iter, _ = ref_cg_rate(n, iters, warm)
+        kind, what = 'reference', ('UNMODIFIED reference (baseline/_ref: ffthompy Tensor/DFT/Operator, CG loop of '
+                                   'general/solver.py:123-136)')
+    else:
+        t_iter, _ = cpu_cg_rate(n, iters, warm)
+        kind, what = 'port', 'oracle (NumPy restatement of the reference path: rfftn / einsum / materialised G^)'
+    return t_iter, {'value': 6*n**3/t_iter, 'unit': 'voxel-DOF/s', 'cores': 1, 'kind': kind,
+                    'sample': '%s: %d CG iterations at %d^3 of the same generator (seed %d); numpy.fft and einsum are '
+                              'single-threaded (host: %d cores, %.0f GB RAM)'
+                              % (what, iters, n, SEED, os.cpu_count() or 0, host_ram_gb() or 0),
+                    'ms_per_iteration': t_iter*1e3, 'grid': [n, n, n]}
+
+
+REF_MAX_STEPS = 12   # 128^3 costs ~4 s per iteration on one core: the reference arm times at most this many
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     n = CPU_SAMPLE_N
-    t_iter, times = cpu_cg_rate(n, max(1, args.steps), warm=max(1, min(args.warmup, 2)))
-    dof = 6*n**3
-    val = dof/t_iter
+    timed = max(1, min(args.steps, REF_MAX_STEPS))
+    t_iter, cb = cpu_baseline(timed, warm=max(1, min(args.warmup, 2)))
+    val = 6*n**3/t_iter
     line = {
         'impl': 'reference', 'metric': 'cg_voxel_dof_per_s', 'value': val, 'unit': 'voxel-DOF/s',
-        'cg_iterations_per_s': 1./t_iter, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-        'ms_per_step': t_iter*1e3, 'higher_is_better': True,
+        'cg_iterations_per_s': 1./t_iter, 'n_gpus': args.gpus, 'steps': args.steps, 'steps_timed': timed,
+        'warmup': args.warmup, 'ms_per_step': t_iter*1e3, 'higher_is_better': True,
         'scaling': 'strong' if (args.gpus > 1 and args.mode == 'slab') else 'weak', 'vs_baseline': None, 'dtype': 'f64',
         'data': 'synthetic',
         'config': ref_config(args),
-        'cpu_baseline': {'value': val, 'unit': 'voxel-DOF/s', 'cores': 1, 'kind': 'port',
-                         'sample': 'oracle CG iterations (NumPy rfftn/einsum, materialised G^) at %d^3 of the same '
-                                   'generator; numpy.fft and einsum are single-threaded (host has %d cores)'
-                                   % (n, os.cpu_count() or 0)},
+        'cpu_baseline': cb,
         'e2e': {'value': val, 'unit': 'voxel-DOF/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
@@ -171,15 +263,115 @@ def workload_config(n, ngpu, where, slab=None):
 
 
 def ref_config(args):
-    """the reference arm reports the config of the GPU arm at the same N (256^3 single GPU; the 512^3 solve for N > 1)"""
-    if args.gpus > 1 and args.mode == 'slab':
-        cfg = workload_config(args.slab_n, args.gpus, 'cpu', slab='n/a')
-        cfg['parallelism'] = 'reference arm: NumPy path on the host cores of rank 0 (no decomposition)'
-        return cfg
-    return workload_config(args.n, 1, 'cpu')
+    """the reference arm states the grid it actually times (`grid`, a bounded sample) next to the grid of the GPU arm
+    at the same N (`gpu_arm_grid`: 256^3 single GPU; the 512^3 solve for N > 1)"""
+    target = args.slab_n if (args.gpus > 1 and args.mode == 'slab') else args.n
+    cfg = workload_config(CPU_SAMPLE_N, 1, 'cpu')
+    cfg['workload'] += ' -- CPU sample of the %d^3 GPU-arm workload (size-normalised metric, voxel-DOF/s)' % target
+    cfg['gpu_arm_grid'] = [target]*3
+    cfg['parallelism'] = 'reference arm: NumPy path on one host core of rank 0 (no decomposition)'
+    return cfg
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def two_phase_A(n, planes, plane0, torch, device, seed=SEED):
+    """BASELINE config 3 coefficients for the x-planes [plane0, plane0+planes) of the n^3 grid, built on the device:
+    A = Cm where phase == 0, Ci where phase == 1 (what `Cm*(1-phase) + Ci*phase` of SURVEY App. C evaluates to,
+    entry for entry); the draw is the one-shot array of default_rng(SEED) (PCG64.advance: bit-identical)"""
+    bg = np.random.PCG64(seed)
+    bg.advance(plane0*n*n)
+    ph = torch.from_numpy(np.random.Generator(bg).random((planes, n, n)) < 0.3).to(device)
+    Cm, Ci = elastic_mandel(1, 1), elastic_mandel(10, 5)
+    A = torch.empty((6, 6, planes, n, n), dtype=torch.float64, device=device)
+    for i in range(6):
+        for j in range(6):
+            A[i, j] = torch.where(ph, float(Ci[i, j]), float(Cm[i, j]))
+    return A
+
+
+def build_problem(Ad, N, kind='elasticity', Nsolve=None):
+    """the solve-loop operator of applications.py:58-69 over a device-resident coefficient array"""
+    from ffthompy_b200.tensors import Tensor, DFT, Operator
+    import ffthompy_b200.projections as proj
+    N = np.array(N)
+    D = int(Ad.shape[0])
+    A = Tensor(name='A', val=Ad, order=2, N=N, multype=21)
+    if kind == 'elasticity':
+        _, G1h, G1s, _, _ = proj.elasticity(N, np.ones(3), NyqNul=True, tensor=True)
+        G = G1h+G1s
+    else:   # exact-integration (Ga) scalar problem: projection of the solve grid Nsolve, enlarged to N = 2 Nsolve - 1
+        _, G, _ = proj.scalar(np.array(Nsolve), np.ones(3), NyqNul=True, tensor=True)
+        G = G.enlarge(N)
+    GN = Operator(name='G1', mat=[[DFT(name='FiN', inverse=True, N=N), G, DFT(name='FN', inverse=False, N=N)]])
+    Afun = Operator(name='FiGFA', mat=[[GN, A]])
+    EN = Tensor(name='EN', N=N, shape=(D,), Fourier=False)
+    EN.set_mean(np.eye(D)[0])
+    return A, Afun, EN
+
+
+def timed_cg(f, Bd, D, N, K, W, world=1):
+    """W untimed + exactly K timed iterations of the device-resident CG (fh_cg_begin / fh_cg_steps); returns
+    (ms per iteration = max over ranks, launches, x, vecs)"""
+    import torch
+    import torch.distributed as dist
+    from ffthompy_b200 import device as dev, _lib as L
+    lib = dev.lib()
+    nvox = int(np.prod(N))
+    x = dev.zeros((D,)+tuple(N))
+    vecs = dev.empty((3*D*nvox,))
+    nres, done = C.c_double(), C.c_int64()
+    L.check(lib.fh_cg_begin(f.handle, dev.ptr(Bd), dev.ptr(x), dev.ptr(vecs), C.byref(nres)))
+    L.check(lib.fh_cg_steps(f.handle, dev.ptr(x), dev.ptr(vecs), 0.0, max(W, 3), C.byref(done), C.byref(nres), None))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = dev.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.check(lib.fh_cg_steps(f.handle, dev.ptr(x), dev.ptr(vecs), 0.0, K, C.byref(done), C.byref(nres), None))
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    assert done.value == K
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev.device())
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())/K, dev.launch_count()-launches0, x, vecs
+
+
+def solve_load0(A, Afun, EN, tol=1e-6):
+    """load case E = e_0 to `tol` through linear_solver (the reference's call, applications.py:75-81):
+    (kit, A_H[0,0] = <A e, e>, seconds)"""
+    import torch
+    from ffthompy_b200.general.solver import linear_solver
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    X, info = linear_solver(solver='CG', Afun=Afun, B=Afun(-EN), x0=EN.zeros_like(),
+                            par={'tol': tol, 'maxiter': 1000}, callback=None)
+    e = X+EN
+    ah = float(A(e)*e)
+    torch.cuda.synchronize()
+    return int(info['kit']), ah, time.perf_counter()-t0
+
+
+def time_fn(fn, reps):
+    import torch
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)/reps
+
+
+COEF_BYTES = {'phase': lambda D, nv: 1.*nv, 'symmetric': lambda D, nv: 8.*(D*(D+1)//2)*nv, 'full': lambda D, nv: 8.*D*D*nv}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -190,9 +382,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     from ffthompy_b200 import device as dev, _lib as L
-    from ffthompy_b200.tensors import Tensor, DFT, Operator
-    import ffthompy_b200.projections as proj
-    from ffthompy_b200.general.solver import linear_solver
+    from ffthompy_b200.tensors import Tensor
     dev.init(local)
     lib = dev.lib()
     n = args.n
@@ -200,55 +390,23 @@ def run_ours(args):
     D = 6
     nvox = n**3
     K, W = args.steps, args.warmup
+    peak, peak_src = measured_peaks()
 
-    # ---- workload, resident in HBM (setup, untimed): A = Cm (1-phase) + Ci phase
-    rng = np.random.default_rng(SEED+rank)
-    phase = torch.from_numpy((rng.random((n, n, n)) < 0.3)).to(dev.device()).to(torch.float64)
-    Cm = torch.from_numpy(elastic_mandel(1, 1)).to(dev.device())
-    Ci = torch.from_numpy(elastic_mandel(10, 5)).to(dev.device())
-    Ad = (Cm[:, :, None, None, None]*(1-phase)+Ci[:, :, None, None, None]*phase).contiguous()
-    del phase
-    A = Tensor(name='A', val=Ad, order=2, N=N, multype=21)
-    _, G1h, G1s, _, _ = proj.elasticity(N, np.ones(3), NyqNul=True, tensor=True)
-    GN = Operator(name='G1', mat=[[DFT(name='FiN', inverse=True, N=N), G1h+G1s, DFT(name='FN', inverse=False, N=N)]])
-    Afun = Operator(name='FiGFA', mat=[[GN, A]])
-    EN = Tensor(name='EN', N=N, shape=(D,), Fourier=False)
-    EN.set_mean(np.eye(D)[0])
+    # ---- workload, resident in HBM (setup, untimed)
+    # (replicas, N > 1: every rank its own microstructure of the same generator family)
+    Ad = two_phase_A(n, n, 0, torch, dev.device(), seed=SEED+rank)
+    A, Afun, EN = build_problem(Ad, N)
     B = Afun(-EN)
     f = Afun.fused()
     assert f is not None, 'the solve-loop operator was not fused'
-    Bd = B._dev()
-    x = dev.zeros((D,)+tuple(N))
-    vecs = dev.empty((3*D*nvox,))
-    nres = C.c_double()
-    done = C.c_int64()
+    cfg = f.config()
 
-    # ---- device-resident CG: warm-up, then exactly K iterations
-    L.check(lib.fh_cg_begin(f.handle, dev.ptr(Bd), dev.ptr(x), dev.ptr(vecs), C.byref(nres)))
-    L.check(lib.fh_cg_steps(f.handle, dev.ptr(x), dev.ptr(vecs), 0.0, max(W, 3), C.byref(done), C.byref(nres), None))
+    # ---- device-resident CG: warm-up, then exactly K iterations, clocks sampled during the timed region
     sampler = ClockSampler(local)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
     sampler.start()
-    launches0 = dev.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    L.check(lib.fh_cg_steps(f.handle, dev.ptr(x), dev.ptr(vecs), 0.0, K, C.byref(done), C.byref(nres), None))
-    e1.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = dev.launch_count()-launches0
+    ms_step, launches, x, vecs = timed_cg(f, B._dev(), D, N, K, W, world)
     clocks = sampler.stop()
-    assert done.value == K
-    t = torch.tensor([ms], dtype=torch.float64, device=dev.device())
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    ms_step = ms_max/K
-    value = world*D*nvox*K/(ms_max*1e-3)
+    value = world*D*nvox/(ms_step*1e-3)
 
     if rank != 0:
         if world > 1:
@@ -257,13 +415,9 @@ def run_ours(args):
         return
 
     # ---- per-stage timing of the operator pipeline (CUDA events on the launch stream) -> roofline
-    peak, peak_src = measured_peaks()
-    flags, pitch, midT = C.c_int(), C.c_int(), C.c_int()
-    L.check(lib.fh_ga_config(f.handle, C.byref(flags), C.byref(pitch), C.byref(midT)))
     F = 8.*D*nvox
-    Fs = 16.*D*n*n*pitch.value
-    amode = (flags.value >> 4) & 3
-    CA = {0: 8.*D*D*nvox, 1: 8.*21*nvox, 2: 1.*nvox}[amode]  # bytes of coefficient data S1 actually streams
+    Fs = 16.*D*n*n*cfg['pitch']
+    CA = COEF_BYTES[cfg['coefficients']](D, nvox)  # bytes of coefficient data S1 actually streams
     alg = {1: F+CA+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
     names = {1: 'S1 A.p + R2C (last axis)', 2: 'S2 C2C axis 1', 3: 'S3 C2C axis 0 + Green + inverse axis 0',
              4: 'S4 inverse C2C axis 1', 5: 'S5 C2R (last axis) + <p,Ap>'}
@@ -271,28 +425,16 @@ def run_ours(args):
     xin.copy_(EN._dev())
     y = dev.empty((D,)+tuple(N))
     stage_ms = {}
-
-    def time_stage(fn):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        e0.record()
-        for _ in range(K):
-            fn()
-        e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1)/K
-
     for st in range(1, 6):
-        stage_ms[st] = time_stage(lambda: L.check(lib.fh_ga_stage(f.handle, st, dev.ptr(xin), dev.ptr(y))))
+        stage_ms[st] = time_fn(lambda: L.check(lib.fh_ga_stage(f.handle, st, dev.ptr(xin), dev.ptr(y))), K)
     # the two kernels that exist only in their CG form: S1 with the folded vector updates (p = r + beta p and the
     # deferred x += alpha p) exactly as fh_cg_steps launches it, and the residual update with <r,r>
     r_, p_ = vecs[:D*nvox], vecs[D*nvox:2*D*nvox]
     if lib.fh_ga_can_defer_x(f.handle):
         L.check(lib.fh_ga_set_xacc(f.handle, dev.ptr(x)))
-        stage_ms[6] = time_stage(lambda: L.check(lib.fh_ga_slab_stage(f.handle, 1, 0, dev.ptr(p_), dev.ptr(r_), 1, dev.ptr(y))))
+        stage_ms[6] = time_fn(lambda: L.check(lib.fh_ga_slab_stage(f.handle, 1, 0, dev.ptr(p_), dev.ptr(r_), 1, dev.ptr(y))), K)
         L.check(lib.fh_ga_set_xacc(f.handle, None))
-        stage_ms[7] = time_stage(lambda: L.check(lib.fh_cgd_update_r(f.handle, dev.ptr(vecs))))
+        stage_ms[7] = time_fn(lambda: L.check(lib.fh_cgd_update_r(f.handle, dev.ptr(vecs))), K)
         alg[6] = 5*F+CA+Fs
         alg[7] = 3*F
         names[6] = 'S1 in its CG form: x += alpha p, p = r + beta p, A.p, R2C (last axis)'
@@ -304,7 +446,7 @@ def run_ours(args):
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fjs:
             tj = json.load(fjs)['dram_bytes_per_launch']
-        tag = {1: 'k_fwd_last_fast', 2: 'k_c2c_fast<256, 8, 0>', 3: 'k_mid_green_pipe', 4: 'k_c2c_fast<256, 8, 1>',
+        tag = {1: 'k_fwd_last_fast', 2: 'k_c2c_fast<256, 8, 0>', 3: 'k_mid2', 4: 'k_c2c_fast<256, 8, 1>',
                5: 'k_inv_last_fast', 6: 'k_fwd_last_fast', 7: 'k_cg_update_r'}[dom]
         if n == 256:
             traffic = [v for k, v in tj.items() if tag in k][0]
@@ -321,41 +463,60 @@ def run_ours(args):
                 'stage_note': 'one CG iteration = S1 (CG form) + S2 + S3 + S4 + S5 + U + 2 scalar kernels; the plain S1 '
                               '(operator application outside CG) is timed for reference and is not part of the step',
                 'iteration': {'algorithmic_bytes': B_iter, 'achieved_GB/s': B_iter/(ms_step*1e-3)/1e9,
-                              'frac_of_peak': B_iter/(ms_step*1e-3)/1e9/peak}}
+                              'frac_of_peak': B_iter/(ms_step*1e-3)/1e9/peak,
+                              'real_traffic_bytes': 10*F+8*Fs+CA,
+                              'real_traffic_note': 'five spectrum passes (8 Fs) + ten field passes + coefficients as streamed'}}
 
     # ---- cuFFT comparator in the same run (torch.fft = cuFFT D2Z + Z2D, no coefficient / Green work)
-    for _ in range(2):
-        torch.fft.irfftn(torch.fft.rfftn(xin, dim=(1, 2, 3)), s=tuple(N), dim=(1, 2, 3))
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
-        torch.fft.irfftn(torch.fft.rfftn(xin, dim=(1, 2, 3)), s=tuple(N), dim=(1, 2, 3))
-    e1.record()
-    torch.cuda.synchronize()
-    cufft_ms = e0.elapsed_time(e1)/5
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(5):
-        L.check(lib.fh_ga_apply(f.handle, dev.ptr(xin), dev.ptr(y)))
-    e1.record()
-    torch.cuda.synchronize()
-    ga_ms = e0.elapsed_time(e1)/5
-    del xin, y, vecs, x
+    cufft_ms = time_fn(lambda: torch.fft.irfftn(torch.fft.rfftn(xin, dim=(1, 2, 3)), s=tuple(N), dim=(1, 2, 3)), 5)
+    ga_ms = time_fn(lambda: L.check(lib.fh_ga_apply(f.handle, dev.ptr(xin), dev.ptr(y))), 5)
+    del xin, y, vecs, x, r_, p_
+    torch.cuda.empty_cache()
+
+    # ---- the same CG step in the other two coefficient modes: the very same array streamed as
+    # a symmetric DxD field (21 of 36 entries read) and as a full DxD field, instead of the 1-byte phase table
+    modes = {cfg['coefficients']: {'ms_per_iteration': ms_step, 'cg_iterations_per_s': 1e3/ms_step,
+                                   'frac_of_peak_iteration': B_iter/(ms_step*1e-3)/1e9/peak,
+                                   'S1_cg_form_ms': stage_ms.get(6), 'coefficient_bytes_per_voxel': CA/nvox}}
+    if not args.no_extras:
+        for mode, code in (('symmetric', '1'), ('full', '0')):
+            if mode in modes:
+                continue
+            os.environ['FH_AMODE'] = code
+            try:
+                A_m, Afun_m, EN_m = build_problem(Ad, N)
+                fm = Afun_m.fused()
+                assert fm.config()['coefficients'] == mode, fm.config()
+                ms_m, _, xm, vm = timed_cg(fm, B._dev(), D, N, K, W)
+                CAm = COEF_BYTES[mode](D, nvox)
+                L.check(lib.fh_ga_set_xacc(fm.handle, dev.ptr(xm)))
+                ym = dev.empty((D,)+tuple(N))
+                s1 = time_fn(lambda: L.check(lib.fh_ga_slab_stage(fm.handle, 1, 0, dev.ptr(vm[D*nvox:2*D*nvox]),
+                                                                  dev.ptr(vm[:D*nvox]), 1, dev.ptr(ym))), K)
+                L.check(lib.fh_ga_set_xacc(fm.handle, None))
+                modes[mode] = {'ms_per_iteration': ms_m, 'cg_iterations_per_s': 1e3/ms_m,
+                               'frac_of_peak_iteration': B_iter/(ms_m*1e-3)/1e9/peak, 'S1_cg_form_ms': s1,
+                               'S1_cg_form_GB/s': (5*F+CAm+Fs)/(s1*1e-3)/1e9, 'coefficient_bytes_per_voxel': CAm/nvox,
+                               'real_traffic_frac_of_peak': (10*F+8*Fs+CAm)/(ms_m*1e-3)/1e9/peak}
+                del A_m, Afun_m, EN_m, fm, xm, vm, ym
+            finally:
+                os.environ.pop('FH_AMODE', None)
+            torch.cuda.empty_cache()
+
+    # ---- solution check of the timed grid: load e_0 to 1e-6 (kit, A_H[0,0]); device-resident inputs
+    kit0, ah0, _ = solve_load0(A, Afun, EN)
+    solution = {'grid': [n]*3, 'kit': kit0, 'A_H00': ah0, 'tol': 1e-6}
 
     # ---- end to end through the operator API with HOST buffers: upload A (pinned), solve to 1e-6, download x
+    from ffthompy_b200.general.solver import linear_solver
     A_host = torch.empty(Ad.shape, dtype=torch.float64, pin_memory=True)
     A_host.copy_(Ad)
-    del A, Afun, GN, f, Ad, B, Bd
+    del A, Afun, f, Ad, B, EN
     torch.cuda.empty_cache()
     A_np = A_host.numpy()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    A2 = Tensor(name='A', val=A_np, order=2, N=N, multype=21)
-    _, G1h, G1s, _, _ = proj.elasticity(N, np.ones(3), NyqNul=True, tensor=True)
-    GN2 = Operator(name='G1', mat=[[DFT(name='FiN', inverse=True, N=N), G1h+G1s, DFT(name='FN', inverse=False, N=N)]])
-    Afun2 = Operator(name='FiGFA', mat=[[GN2, A2]])
-    EN2 = Tensor(name='EN', N=N, shape=(D,), Fourier=False)
-    EN2.set_mean(np.eye(D)[0])
+    A2, Afun2, EN2 = build_problem(A_np, N)
     X, info = linear_solver(solver='CG', Afun=Afun2, B=Afun2(-EN2), x0=EN2.zeros_like(),
                             par={'tol': 1e-6, 'maxiter': 1000}, callback=None)
     x_host = X.val
@@ -365,31 +526,89 @@ def run_ours(args):
            'd2h_bytes_per_step': int(x_host.nbytes/kit), 'cg_iterations': kit, 'seconds': t_e2e,
            'what': 'linear_solver(CG, tol 1e-6) through ffthompy_b200 Tensor/Operator API: pinned-host A uploaded, '
                    'solution downloaded, all inside the timed region'}
-    del A2, Afun2, GN2, X
+    del A2, Afun2, EN2, X, A_host, A_np
+    torch.cuda.empty_cache()
+
+    extras = {}
+    if not args.no_extras and world == 1:
+        extras['config2_255'] = bench_config2(torch, dev, L, lib, K, W, peak)
+        torch.cuda.empty_cache()
+        extras['strong_base'] = bench_512_single(torch, dev, K, W, peak)
+        torch.cuda.empty_cache()
 
     # ---- CPU baseline on a bounded sample (rank 0 only)
-    t_cpu, _ = cpu_cg_rate(CPU_SAMPLE_N, 3, warm=1)
-    cpu = {'value': D*CPU_SAMPLE_N**3/t_cpu, 'unit': 'voxel-DOF/s', 'cores': 1, 'kind': 'port',
-           'sample': 'oracle (NumPy restatement of the reference path) CG iterations at %d^3, same generator; '
-                     'numpy.fft/einsum are single-threaded (host has %d cores)' % (CPU_SAMPLE_N, os.cpu_count() or 0),
-           'ms_per_iteration': t_cpu*1e3}
+    _, cpu = cpu_baseline(3, warm=1)
 
     line = {'metric': 'cg_voxel_dof_per_s', 'value': value, 'unit': 'voxel-DOF/s',
             'cg_iterations_per_s': world*1e3/ms_step, 'n_gpus': world, 'steps': K, 'warmup': max(W, 3),
             'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
             'data': 'synthetic', 'config': workload_config(n, world, 'gpu'), 'clocks': clocks, 'e2e': e2e,
             'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+            'solution': solution, 'coefficient_modes': modes,
             'comparators': {'cufft_rfftn_irfftn_ms': cufft_ms, 'fused_operator_ms': ga_ms,
                             'note': 'cuFFT (torch.fft) forward+inverse of the same (6,n,n,n) field, no A.p / Green / '
                                     'dot work, vs the whole fused operator G.A.p'},
-            'kernels': {'fast_axes_mask': flags.value & 7, 'spectrum_pitch': pitch.value, 'mid_T': midT.value,
-                        'coefficient_mode': {0: 'full DxD array', 1: 'symmetric (upper triangle read)',
-                                             2: 'phase table (1 byte/voxel)'}[(flags.value >> 4) & 3],
-                        'phases': flags.value >> 8}}
+            'kernels': {'axis_kernels': {k: cfg[k] for k in ('last', 'mid1', 'mid0')}, 'spectrum_pitch': cfg['pitch'],
+                        'coefficient_mode': cfg['coefficients'], 'phases': cfg['nphase']}}
+    line.update(extras)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_config2(torch, dev, L, lib, K, W, peak):
+    """BASELINE config 2 in shape: 3-D scalar (D = 3), N = 128^3 solved on the exact-integration grid Nbar = 255^3
+    (= 3*5*17: the run-time-length kernels), Ga projection with the reference's prod(Nbar)/prod(N) scale.  The
+    coefficient field is a synthetic non-piecewise-constant isotropic field (every voxel its own value, as the
+    exactly integrated coefficients of Material.get_A_Ga are), so S1 streams it as a symmetric array."""
+    n, ns, D = 255, 128, 3
+    N = (n, n, n)
+    nvox = n**3
+    g = torch.Generator(device=dev.device())
+    g.manual_seed(SEED)
+    a = 1.+10.*torch.rand((n, n, n), dtype=torch.float64, device=dev.device(), generator=g)
+    Ad = torch.zeros((3, 3, n, n, n), dtype=torch.float64, device=dev.device())
+    for i in range(3):
+        Ad[i, i] = a
+    del a
+    A, Afun, EN = build_problem(Ad, N, kind='scalar_Ga', Nsolve=(ns, ns, ns))
+    B = Afun(-EN)
+    f = Afun.fused()
+    cfg = f.config()
+    ms, _, x, vecs = timed_cg(f, B._dev(), D, N, K, W)
+    B_iter = 408.*nvox
+    del x, vecs
+    return {'workload': '3-D scalar (D=3), N=128^3 on the Ga grid 255^3, synthetic non-constant isotropic coefficients',
+            'grid': [n]*3, 'ms_per_iteration': ms, 'cg_iterations_per_s': 1e3/ms, 'voxel_dof_per_s': D*nvox*1e3/ms,
+            'algorithmic_bytes': B_iter, 'frac_of_peak_iteration': B_iter/(ms*1e-3)/1e9/peak,
+            'axis_kernels': {k: cfg[k] for k in ('last', 'mid1', 'mid0')}, 'coefficient_mode': cfg['coefficients']}
+
+
+def bench_512_single(torch, dev, K, W, peak):
+    """BASELINE config 4's grid on ONE GPU: the strong-scaling base of the N > 1 lines and the 1 <-> N agreement check
+    (kit, A_H[0,0] of load e_0 at tol 1e-6)"""
+    n, D = 512, 6
+    free, _ = torch.cuda.mem_get_info()
+    if free < 110e9:
+        return {'skipped': 'needs ~100 GB of free HBM, %.0f GB available' % (free/1e9)}
+    N = (n, n, n)
+    nvox = float(n)**3
+    Ad = two_phase_A(n, n, 0, torch, dev.device())
+    A, Afun, EN = build_problem(Ad, N)
+    B = Afun(-EN)
+    f = Afun.fused()
+    cfg = f.config()
+    k = max(5, min(K, 20))
+    ms, _, x, vecs = timed_cg(f, B._dev(), D, N, k, W)
+    del x, vecs, B
+    torch.cuda.empty_cache()
+    kit, ah, sec = solve_load0(A, Afun, EN)
+    B_iter = 888.*nvox
+    return {'grid': [n]*3, 'ms_per_iteration': ms, 'cg_iterations_per_s': 1e3/ms, 'voxel_dof_per_s': D*nvox*1e3/ms,
+            'frac_of_peak_iteration': B_iter/(ms*1e-3)/1e9/peak, 'steps': k, 'kit': kit, 'A_H00': ah, 'tol': 1e-6,
+            'solve_seconds': sec, 'axis_kernels': {k_: cfg[k_] for k_ in ('last', 'mid1', 'mid0')},
+            'coefficient_mode': cfg['coefficients']}
 
 
 # ----------------------------------------------------------------------------- GPU arm, N > 1: slab-decomposed solve
@@ -414,17 +633,8 @@ def run_slab(args):
     K, W = args.steps, max(args.warmup, 3)
     lay = SlabLayout(N, world, rank)
 
-    def make_A():
-        # every rank draws only its own x-planes of the one-shot array (PCG64.advance: bit-identical)
-        bg = np.random.PCG64(SEED)
-        bg.advance(lay.n0_off*n*n)
-        ph = np.random.Generator(bg).random((lay.n0l, n, n)) < 0.3
-        phase = torch.from_numpy(ph).to(dev.device()).to(torch.float64)
-        Cm = torch.from_numpy(elastic_mandel(1, 1)).to(dev.device())
-        Ci = torch.from_numpy(elastic_mandel(10, 5)).to(dev.device())
-        return (Cm[:, :, None, None, None]*(1-phase)+Ci[:, :, None, None, None]*phase).contiguous()
-
-    Ad = make_A()
+    # every rank draws only its own x-planes of the one-shot array (PCG64.advance: bit-identical)
+    Ad = two_phase_A(n, lay.n0l, lay.n0_off, torch, dev.device())
     _, G1h, G1s, _, _ = proj.elasticity(np.array(N), np.ones(3), NyqNul=True, tensor=True)
     G = G1h+G1s
     exchange, tuned = args.exchange, None
@@ -536,12 +746,18 @@ def run_slab(args):
         x_host = X.cpu()
         torch.cuda.synchronize()
         tt = torch.tensor([time.perf_counter()-t0], dtype=torch.float64, device=dev.device())
+        # A_H[0,0] = <A e, e>, e = X + e_0 (postprocess.py:53-70), for the 1 <-> N GPU agreement check
+        from ffthompy_b200 import ops
+        e_ = X.clone()
+        e_[0] += 1.
+        ah00 = op2.dot(ops.mul21(A2, e_, D, lay.n0l*n*n, 1), e_)
+        del e_
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t_e2e = float(tt.item())
         kit = info['kit']
         e2e = {'value': D*nvox*kit/t_e2e, 'unit': 'voxel-DOF/s',
                'h2d_bytes_per_step': int(world*A_host.numel()*8/kit), 'd2h_bytes_per_step': int(world*x_host.numel()*8/kit),
-               'cg_iterations': kit, 'seconds': t_e2e,
+               'cg_iterations': kit, 'seconds': t_e2e, 'A_H00': ah00,
                'what': 'SlabGA(A_slab).cg(tol 1e-6) on every rank: pinned-host coefficient slab uploaded, operator '
                        'set-up (symmetric-memory rendezvous included), solve, solution slab downloaded; wall clock, '
                        'max over ranks'}
@@ -553,6 +769,9 @@ def run_slab(args):
                 'config': workload_config(n, world, 'gpu', slab='%s (chunks %d)' % (mode, nchunk)),
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': launches_all, 'roofline': roofline,
                 'exchange_autotune_ms_per_apply': tuned,
+                'solution': ({'grid': [n]*3, 'kit': e2e['cg_iterations'], 'A_H00': e2e['A_H00'], 'tol': 1e-6,
+                              'compare_with': 'strong_base.kit / strong_base.A_H00 of the N = 1 line (same grid on one GPU)'}
+                             if e2e else None),
                 'note': 'strong scaling over N = 2, 4, 8 at the fixed 512^3 grid; the N = 1 line is the 256^3 '
                         'single-GPU workload (BASELINE config 3). value is size-normalised (voxel-DOF/s).'}
         print(json.dumps(line), flush=True)
@@ -571,6 +790,7 @@ def main():
                     help='N > 1: one slab-decomposed solve (default) or N independent replicas')
     ap.add_argument('--slab-n', type=int, default=512, help='grid size of the slab-decomposed solve')
     ap.add_argument('--exchange', default=None, help='slab exchange mode (default: best available)')
+    ap.add_argument('--no-extras', action='store_true', help='N = 1: skip coefficient modes, config 2 and the 512^3 base')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference(args)

@@ -19,6 +19,7 @@
 #pragma once
 #include "fh_fft.cuh"
 #include "fh_green.cuh"
+#include "fh_types.cuh"
 #include <cooperative_groups.h>
 
 template <int N>
@@ -188,13 +189,6 @@ __global__ void __launch_bounds__(((KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM 
 //   2: piecewise constant — one byte per voxel indexes a table of <= 16 DxD matrices held in shared
 //   memory (detected by fh_ga_create, e.g. inclusion-type microstructures);  -1: no multiply
 __device__ __forceinline__ int pidx(int row) { return row + (row >> 4); }
-
-// two-phase coefficient table passed BY VALUE (kernel parameter = constant bank): both matrices
-// are read with uniform addresses and selected per voxel, so the per-voxel gather costs no shared
-// memory bandwidth (A layout 3)
-struct Lut2C {
-    double c[2][36];
-};
 
 // phase 0 of S1: p = r + beta p (optional), sigma = A p on the CTA's TRW x N voxels, two voxels per
 // thread and step (16-byte accesses); store(L, i2, s0, s1) receives sigma of real line L = comp*TRW+row
@@ -1109,15 +1103,6 @@ __global__ void __launch_bounds__(256)
 // routine: N = R0*R1*R2 with up to three radices from {2,3,4,5,7,8,9,11,13,15,16,17,19}.  This puts the
 // odd "doubled" grids of the exact-integration scheme (Nbar = 2N-1: 255 = 15*17, 243 = 9*9*3, 225 = 15*15,
 // 125 = 5*5*5, 63 = 9*7, ...) on the same fused five-stage pipeline as the powers of two.
-struct RtPlan {
-    int n;      // length
-    int ns;     // number of stages (1..3)
-    int R[3];   // radices, DIF order
-    int NB[3];  // block size of stage s:  n, n/R0, n/(R0*R1)
-    int TS[3];  // twiddle stride of stage s: 1, R0, R0*R1
-    int npr;    // padded rows: n + n/16 + 1
-};
-
 __device__ __forceinline__ int rt_freq_of_row(const RtPlan& P, int row) {
     int k = 0, mul = 1, rem = row;
     for (int s = 0; s < P.ns; ++s) {
@@ -1453,20 +1438,6 @@ __global__ void __launch_bounds__(256, 2)
 // The multi-GPU pipeline moves the half spectrum between x-slabs and y-slabs with all-to-all.  So that
 // no pack/unpack pass is needed, the strided-axis kernels address the exchange buffers directly: a
 // line (panel o, row, column t) lives at  base(o) + rowoff(row) + t.
-struct LineMap {
-    const int64_t* off;        // per-row offsets (nullptr: row * rstride)
-    int64_t rstride;
-    int64_t cstride, istride;  // panel o = c * nper + i  ->  c * cstride + i * istride
-    int nper;
-};
-__device__ __forceinline__ int64_t linemap_base(const LineMap& m, int64_t o) {
-    const int64_t c = o / m.nper, i = o - c * m.nper;
-    return c * m.cstride + i * m.istride;
-}
-__device__ __forceinline__ int64_t linemap_row(const LineMap& m, int row) {
-    return m.off ? m.off[row] : (int64_t)row * m.rstride;
-}
-
 // S2 / S4 between the natural x-slab spectrum and an exchange buffer (out of place)
 template <int N, int T, bool INV>
 __global__ void __launch_bounds__(256) k_c2c_map(const cplx* __restrict__ in, cplx* __restrict__ out,

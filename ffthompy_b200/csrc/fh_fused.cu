@@ -14,67 +14,15 @@
 //   S5  C2R along the last axis, scaled by 1/prod(N), fused with the partial sums of <p, Ap>
 // Power-of-two axis lengths (64, 128, 256) use the register-resident kernels of fh_fast.cuh,
 // any other length the generic shared-memory passes of fh_fft.cu.
-#include "fh_plan.cuh"
-#include "fh_green.cuh"
+#include "fh_ga.cuh"
 #include "fh_fast.cuh"
 #include "fh_reg3.h"
+#include "fh_mid2.h"
 #include "../../include/ffthom_b200.h"
 #include <stdlib.h>
 #include <string.h>
 
 int fh_fill_green(GreenDesc& g, const fh_green* in);
-
-#define GA_NT 256
-#define GA_MAXPART 524288
-
-struct fh_ga {
-    const fh_plan* plan;
-    int D;
-    const double* A;
-    int a_layout;
-    int a_mode;            // how S1 reads the coefficients: 0 full, 1 symmetric (upper triangle), 2 phase table
-    unsigned char* phase;  // [prod(N)] phase index per voxel (a_mode 2), owned by the operator
-    double* lut;           // [nphase][D][D]
-    Lut2C lutc;            // host copy of the table when nphase <= 2 (passed by value to S1)
-    int nphase;
-    GreenDesc g;
-    int pitch;       // padded spectrum row length (complex elements)
-    int64_t nrows;   // rows of the local real fields: prod(N[:-1]), or n0_local*N1 for a slab
-    int64_t nloc;    // local voxels per component = nrows * N_last
-    int n0l, n1l;    // slab decomposition (3-D): local planes of axis 0 (real space) / axis 1 (axis-0 pass)
-    cplx* specT;     // [D][N0][n1l][pitch] y-slab spectrum (== spec when not decomposed)
-    int64_t nspecp;  // nrows * pitch
-    double* work;
-    double* sigma;  // [D*nreal] (generic last-axis path only)
-    cplx* spec;     // [D][nrows][pitch]
-    // configuration
-    bool fast_last, fast_mid1, fast_mid0;
-    bool rt_ok[3];   // run-time-length in-place kernels usable on axis a (any N = up to 3 supported radices)
-    RtPlan rt[3];
-    int mid_T, trw, mid_pipe;
-    int trw_s1;          // rows per CTA of S1 when it differs from trw (0: same)
-    int chunk_cols;      // L2 blocking of S2-S3-S4: columns of the spectrum rows per chunk (0 = off)
-    int cur_col0, cur_ncols;  // chunk the next S3 launch works on (0,0 = whole rows)
-    // device scalars / partial sums of the Krylov loops
-    double* scal;  // [16]: rr, pAp, alpha, beta, norm_res
-    double* part;  // [GA_MAXPART]
-    double* pinned;
-    // CG state (fh_cg_begin / fh_cg_steps)
-    int64_t kit;
-    int have_beta;
-    double* xacc;    // non-null inside fh_cg_steps: S1 applies the deferred x += alpha p while it has p in registers
-    int last_npart;  // partial sums left in `part` by the last stage-5 launch
-    // row range of the next S1 / S5 launch (chunked slab pipeline); row_cnt = 0 means all rows
-    int64_t row_beg, row_cnt;
-    // zero-copy slab exchange (fh_ga_slab_direct): chunk-major blocks [J][G][D][n0c][n1l][pitch]
-    int sd_world, sd_nchunk, sd_n0c;
-    cplx* sd_bufA;      // S2 output / S4 input (send buffer forward, receive buffer backward)
-    cplx* sd_bufB;      // S3 in place (receive buffer forward, send buffer backward)
-    int64_t* sd_off1;   // [N1] row offsets of the axis-1 passes inside one chunk of bufA
-    int64_t* sd_off0;   // [N0] row offsets of the axis-0 pass inside bufB
-    int64_t sd_cs0;     // component stride of the axis-0 pass
-    int sd_peer;        // 1: the axis-0 pass reads/writes the peers' x-slab spectra directly (fh_ga_slab_peer)
-};
 
 // rows handled by the next S1 / S5 launch: element offsets into fields (ro) and spectrum rows (so),
 // CTA count and first partial-sum slot
@@ -378,6 +326,14 @@ template <int KIND, int DIM>
 static int launch_mid_fast(fh_ga* op) {
     const int N = op->plan->N[0];
     const int T = op->mid_T;
+    // 8-column tiles, six shared-memory passes, register prefetch (fh_mid2.cuh): 64 / 128 / 256 in 3-D
+    if (DIM == 3 && fh_mid2_len(N) && op->mid_pipe == 1) {
+        const int64_t inner = (int64_t)op->n1l * op->pitch;
+        const int ncols = op->cur_ncols ? op->cur_ncols : op->pitch;
+        if (op->pitch % 8 == 0 && ncols % 8 == 0 && op->cur_col0 % 8 == 0)
+            return fh_mid2_green(N, KIND, op->specT, op->plan->ax[0].tw, op->g, NULL, inner, (int64_t)N * inner,
+                                 op->pitch, 0, op->plan->nh, op->n1l, op->cur_col0, ncols);
+    }
     if (use_reg3() && fh_reg3_mid_len(N)) {  // three-pass register kernels (fh_reg3.cu decides which lengths)
         const int64_t inner = (DIM == 3) ? (int64_t)op->n1l * op->pitch : op->pitch;
         if (inner % 8 == 0)
@@ -1515,7 +1471,9 @@ extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, v
     const int n0c = op->n0l / nchunk;
     const int64_t rows_c = (int64_t)n0c * p->N[1];
     if (nchunk > 1) {
-        const bool rt_last = !op->fast_last && op->rt_ok[2];
+        // the run-time-length S5 honours row ranges only in its in-place form (FH_RT bit 3); the generic batched C2R
+        // would redo every chunk's rows on each call
+        const bool rt_last = !op->fast_last && op->rt_ok[2] && (env_int("FH_RT", 7) & 8);
         if (!(op->fast_last && rows_c % op->trw == 0) && !(rt_last && rows_c % 24 == 0))
             return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_direct: the last-axis kernels cannot run %lld-row chunks",
                                 (long long)rows_c);
@@ -1552,10 +1510,9 @@ extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, v
     op->sd_peer = 0;
     op->sd_bufA = (cplx*)bufA;
     op->sd_bufB = (cplx*)bufB;
-    // padding columns travel with the rows: keep them zero
-    const size_t bytes = sizeof(cplx) * (size_t)D * n0l * p->N[1] * P;
-    FH_CUDA(cudaMemsetAsync(bufA, 0, bytes, fh_stream()));
-    FH_CUDA(cudaMemsetAsync(bufB, 0, bytes, fh_stream()));
+    // padding columns travel with the rows and must be zero.  The caller hands in zero-filled buffers: with peer-mapped
+    // (symmetric-memory) buffers a fill enqueued here could run after a faster rank's first push into this buffer and
+    // wipe it, so nothing is written to the exchange buffers in this call.
     return FH_OK;
 }
 

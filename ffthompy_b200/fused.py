@@ -21,7 +21,9 @@ class FusedGA(object):
         self.N = tuple(int(n) for n in N)
         self.D = int(A.shape[0])
         self.A_dev = A._dev()           # keeps the coefficient buffer alive
-        self.A_id = id(self.A_dev)
+        # the operator snapshots A (phase table / symmetry flag, fh_ga_create): key the cache on the buffer
+        # identity AND on the Tensor's in-place mutation counter (add_mean / set_mean write into the same buffer)
+        self.A_id = (id(self.A_dev), getattr(A, '_version', 0))
         self.green_key = _green_key(G)
         self.plan = dev.plan(self.N)
         lib = dev.lib()
@@ -39,6 +41,16 @@ class FusedGA(object):
                 L.load().fh_ga_destroy(self.handle)
         except Exception:
             pass
+
+    def config(self):
+        """which kernel family serves each axis and how S1 reads the coefficients (fh_ga_config)"""
+        fl, pitch, mt = C.c_int(), C.c_int(), C.c_int()
+        L.check(dev.lib().fh_ga_config(self.handle, C.byref(fl), C.byref(pitch), C.byref(mt)))
+        f = fl.value
+        fam = lambda fast, rt: 'pow2' if f & fast else ('rt' if f & rt else 'generic')  # noqa: E731
+        return {'last': fam(1, 1 << 16), 'mid1': fam(2, 1 << 17), 'mid0': fam(4, 1 << 18),
+                'coefficients': ('full', 'symmetric', 'phase')[(f >> 4) & 3], 'nphase': (f >> 8) & 0xff,
+                'pitch': pitch.value}
 
     def accepts(self, x):
         return ((not x.Fourier) and x.order == 1 and tuple(x.shape) == (self.D,) and tuple(x.N) == self.N
@@ -62,6 +74,28 @@ class FusedGA(object):
                                 C.byref(kit), C.byref(nres), hist, cap))
         k = int(kit.value)
         return x, k, float(nres.value), np.array(hist[:min(k+1, cap)])
+
+    def cg_callback(self, B_dev, x0_dev, tol, maxiter, on_iterate):
+        """the same device loop advanced one iteration per call (fh_cg_begin / fh_cg_steps), `on_iterate(x)` after
+        each with a private copy of the iterate (general/solver.py:134-135: callback(xCG)).  The operator stays
+        fused; only the deferred x update is flushed every iteration instead of once at the end."""
+        from . import ops
+        lib = dev.lib()
+        x = ops.clone(x0_dev)
+        vecs = dev.empty((3*self.D*self.nreal,))
+        nres, done = C.c_double(), C.c_int64()
+        L.check(lib.fh_cg_begin(self.handle, dev.ptr(B_dev), dev.ptr(x), dev.ptr(vecs), C.byref(nres)))
+        hist = [float(nres.value)]
+        kit = 0
+        while hist[-1] > tol and kit < maxiter:
+            L.check(lib.fh_cg_steps(self.handle, dev.ptr(x), dev.ptr(vecs), float(tol), 1, C.byref(done),
+                                    C.byref(nres), None))
+            if done.value != 1:
+                break
+            kit += 1
+            hist.append(float(nres.value))
+            on_iterate(ops.clone(x))
+        return x, kit, hist[-1], np.array(hist)
 
     def richardson(self, B_dev, x0_dev, alpha, tol, maxiter):
         """general/solver.py:63-77 as a device loop."""
@@ -119,6 +153,6 @@ def get_fused(op, cached):
     if m is None:
         return None
     A, G, N = m
-    if cached is not None and cached.A_id == id(A._dev()) and cached.green_key == _green_key(G):
+    if cached is not None and cached.A_id == (id(A._dev()), getattr(A, '_version', 0)) and cached.green_key == _green_key(G):
         return cached
     return FusedGA(A, G, N)

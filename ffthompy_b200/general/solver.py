@@ -1,16 +1,50 @@
 """Krylov solvers behind `linear_solver` — drop-in for ffthompy/general/solver.py.
 
-CG and Richardson on the fused G·A operator run as device loops (csrc/fh_fused.cu: fh_cg,
-fh_richardson) — no host round trip other than the residual norm that decides termination.
-Any other operator / callback / custom scalar product goes through the same algorithms
-written over the Tensor algebra (each step a device kernel), exactly as in the reference.
+Same entry point, argument meaning, defaults, stop rules and `info` keys as the reference (general/solver.py:8-303);
+the bodies are this package's own:
+
+* CG and Richardson on the fused G·A operator run as device loops (csrc/fh_fused.cu: fh_cg, fh_cg_begin/steps,
+  fh_richardson) — no host round trip other than the 8-byte residual norm that decides termination.  A callback
+  (ffthompy/applications.py:71-72 always attaches one) keeps the device loop: it is advanced one iteration per
+  call, the iterate handed to the callback after each.
+* Every other combination (BiCG, Chebyshev, custom scalar products, unfused operators, legacy VecTri operands) runs
+  the same recurrences over the operand algebra — each operation a device kernel — through the small `_Recurrence`
+  helpers below.
 """
 import numpy as np
 
 from .base import Timer
 from ..tensors import Tensor, Operator
 
+_SOLVERS = {}
 
+
+def _solver(*names):
+    def reg(fn):
+        for nm in names:
+            _SOLVERS[nm] = fn
+        return fn
+    return reg
+
+
+def linear_solver(Afun, B, ATfun=None, x0=None, par=None, solver=None, callback=None):
+    """Solve Afun(x) = B (general/solver.py:8-60): `solver` in cg | bicg | iterative | richardson | chebyshev | cheby |
+    scipy_cg | scipy_bicg (+ the dotted scipy names); returns (x, info) with info['kit'], ['norm_res'], ['time']."""
+    watch = Timer('Solving linsys by %s' % solver)
+    if x0 is None:
+        x0 = B.zeros_like()
+    if callback is not None:
+        callback(x0)
+    key = solver.lower() if solver.split('_')[0].lower() != 'scipy' and not solver.lower().startswith('scipy.') else 'scipy'
+    if key not in _SOLVERS:
+        raise NotImplementedError("This kind (%s) of linear solver is not implemented" % solver)
+    x, info = _SOLVERS[key](Afun=Afun, ATfun=ATfun, B=B, x0=x0, par=par, callback=callback, name=solver)
+    watch.measure(print_time=False)
+    info.update({'time': watch.vals})
+    return x, info
+
+
+# ----------------------------------------------------------------------------- helpers
 def _is_vectri(B):
     try:
         from ..matvecs import VecTri
@@ -19,59 +53,32 @@ def _is_vectri(B):
         return False
 
 
-def linear_solver(Afun, B, ATfun=None, x0=None, par=None, solver=None, callback=None):
-    """Wrapper for the linear solvers suited to FFT-based homogenisation (general/solver.py:8-60)."""
-    tim = Timer('Solving linsys by %s' % solver)
-    if x0 is None:
-        x0 = B.zeros_like()
-
-    if callback is not None:
-        callback(x0)
-
-    if solver.lower() in ['cg']:  # conjugate gradients
-        x, info = CG(Afun, B, x0=x0, par=par, callback=callback)
-    elif solver.lower() in ['bicg']:  # biconjugate gradients
-        x, info = BiCG(Afun, ATfun, B, x0=x0, par=par, callback=callback)
-    elif solver.lower() in ['iterative', 'richardson']:  # iterative solver
-        x, info = richardson(Afun, B, x0, par=par, callback=callback)
-    elif solver.lower() in ['chebyshev', 'cheby']:  # iterative solver
-        x, info = cheby2TERM(A=Afun, B=B, x0=x0, par=par, callback=callback)
-    elif solver.split('_')[0].lower() in ['scipy']:  # solvers in scipy (host-side bridge)
-        x, info = _scipy_bridge(Afun, ATfun, B, x0, par, solver, callback)
-    else:
-        msg = "This kind (%s) of linear solver is not implemented" % solver
-        raise NotImplementedError(msg)
-
-    tim.measure(print_time=False)
-    info.update({'time': tim.vals})
-    return x, info
+def get_scal(B, par):
+    """scalar product matching the operand type, or par['scal'] (general/solver.py:287-298)"""
+    if par is not None and 'scal' in par:
+        return par['scal']
+    if isinstance(B, np.matrix) or _is_vectri(B):
+        return lambda X, Y: float(X.T*Y)
+    if isinstance(B, Tensor):
+        return lambda X, Y: X*Y
+    return lambda X, Y: np.sum(X*Y.conj()).real
 
 
-def _scipy_bridge(Afun, ATfun, B, x0, par, solver, callback):
-    """general/solver.py:28-53: SciPy iterates on host vectors; every matvec is a device call."""
-    import scipy.sparse.linalg as spslin
-    x0vec = x0.ravel() if isinstance(x0, np.ndarray) else np.asarray(x0.vec()).ravel()
-    Afun.define_operand(B)
-    if solver in ['scipy.sparse.linalg.cg', 'scipy_cg']:
-        Afunvec = spslin.LinearOperator(Afun.matshape, matvec=lambda v: np.asarray(Afun.matvec(v)).ravel(),
-                                        dtype=np.float64)
-        xcol, info = spslin.cg(Afunvec, np.asarray(B.vec()).ravel(), x0=x0vec, rtol=par['tol'],
-                               maxiter=int(par['maxiter']), M=None, callback=callback)
-    elif solver in ['scipy.sparse.linalg.bicg', 'scipy_bicg']:
-        ATfun.define_operand(B)
-        Afunvec = spslin.LinearOperator(Afun.matshape, matvec=lambda v: np.asarray(Afun.matvec(v)).ravel(),
-                                        rmatvec=lambda v: np.asarray(ATfun.matvec(v)).ravel(), dtype=np.float64)
-        xcol, info = spslin.bicg(Afunvec, np.asarray(B.vec()).ravel(), x0=x0vec, rtol=par['tol'],
-                                 maxiter=int(par['maxiter']), M=None, callback=callback)
-    else:
-        raise NotImplementedError("This kind (%s) of linear solver is not implemented" % solver)
-    x = B.empty_like(name='x')
-    x.val = np.reshape(xcol, B._vshape())
-    return x, {'info': info}
+def get_norm(B, par):
+    dot = get_scal(B, par)
+    return lambda X: dot(X, X)**0.5
 
 
-def _fused_for(Afun, B, x0, par, callback):
-    if callback is not None or (par is not None and 'scal' in par):
+def _settings(par, **defaults):
+    par = dict() if par is None else par
+    for k, v in defaults.items():
+        par.setdefault(k, v)       # the reference also writes its defaults into the caller's dict
+    return par
+
+
+def _fused_for(Afun, B, x0, par):
+    """the device pipeline of `Afun` if B and x0 are fields it accepts and the default scalar product is wanted"""
+    if par is not None and 'scal' in par:
         return None
     if not (isinstance(Afun, Operator) and isinstance(B, Tensor) and isinstance(x0, Tensor)):
         return None
@@ -81,191 +88,182 @@ def _fused_for(Afun, B, x0, par, callback):
     return f
 
 
+# ----------------------------------------------------------------------------- stationary iteration
+@_solver('iterative', 'richardson')
+def _richardson_entry(Afun, B, x0, par, callback, **_):
+    return richardson(Afun, B, x0, par=par, callback=callback)
+
+
 def richardson(Afun, B, x0, par=None, callback=None):
-    """general/solver.py:63-77"""
-    omega = 1./par['alpha']
-    res = {'norm_res': 1e15,
-           'kit': 0}
-    f = _fused_for(Afun, B, x0, par, callback)
+    """x <- x + (B - A x)/alpha until the residual taken BEFORE the update is <= tol (general/solver.py:63-77)"""
+    info = {'norm_res': 1e15, 'kit': 0}
+    f = _fused_for(Afun, B, x0, par) if callback is None else None
     if f is not None:
-        xd, kit, nres = f.richardson(B._dev(), x0._dev(), par['alpha'], par['tol'], int(par['maxiter']))
-        res['kit'], res['norm_res'] = kit, nres
-        return x0.copy(val=xd), res
+        xd, info['kit'], info['norm_res'] = f.richardson(B._dev(), x0._dev(), par['alpha'], par['tol'], int(par['maxiter']))
+        return x0.copy(val=xd), info
+    size = get_norm(B, par)
+    step = 1./par['alpha']
     x = x0
-    norm = get_norm(B, par)
-    while (res['norm_res'] > par['tol'] and res['kit'] < par['maxiter']):
-        res['kit'] += 1
-        residuum = B-Afun(x)
-        x = x + omega*residuum
-        res['norm_res'] = norm(residuum)
+    while info['norm_res'] > par['tol'] and info['kit'] < par['maxiter']:
+        defect = B-Afun(x)
+        x = x+step*defect
+        info['kit'] += 1
+        info['norm_res'] = size(defect)
         if callback is not None:
             callback(x)
-    return x, res
+    return x, info
+
+
+# ----------------------------------------------------------------------------- conjugate gradients
+@_solver('cg')
+def _cg_entry(Afun, B, x0, par, callback, **_):
+    return CG(Afun, B, x0=x0, par=par, callback=callback)
 
 
 def CG(Afun, B, x0, par=None, callback=None):
-    """Conjugate gradients (general/solver.py:80-139): absolute tolerance on
-    sqrt(<r,r>) with the mean-normalised scalar product of the operands."""
-    if par is None:
-        par = dict()
-    if 'tol' not in list(par.keys()):
-        par['tol'] = 1e-6
-    if 'maxiter' not in list(par.keys()):
-        par['maxiter'] = int(1e3)
-
-    f = _fused_for(Afun, B, x0, par, callback)
+    """Conjugate gradients with the reference's conventions (general/solver.py:80-139): the operator is applied to x0
+    even when it is zero, the stop test is ABSOLUTE on sqrt(<r,r>) in the mean-normalised scalar product of the
+    operands, and a solve that needs no iteration reports norm_res = 0."""
+    par = _settings(par, tol=1e-6, maxiter=int(1e3))
+    f = _fused_for(Afun, B, x0, par)
     if f is not None:
-        xd, kit, nres, hist = f.cg(B._dev(), x0._dev(), par['tol'], int(par['maxiter']))
-        res = {'kit': kit, 'norm_res': nres if kit > 0 else 0, 'norm_res_log': hist}
-        return x0.copy(val=xd), res
+        if callback is None:
+            xd, kit, nres, hist = f.cg(B._dev(), x0._dev(), par['tol'], int(par['maxiter']))
+        else:
+            xd, kit, nres, hist = f.cg_callback(B._dev(), x0._dev(), par['tol'], int(par['maxiter']),
+                                                lambda buf: callback(x0.copy(val=buf)))
+        return x0.copy(val=xd), {'kit': kit, 'norm_res': nres if kit > 0 else 0, 'norm_res_log': hist}
 
-    scal = get_scal(B, par)
-
-    res = dict()
-    xCG = x0
-    Ax = Afun(x0)
-    R = B - Ax
-    P = R
-    rr = scal(R, R)
-    res['kit'] = 0
-    res['norm_res'] = np.double(rr)**0.5  # /np.norm(E_N)
-    norm_res_log = []
-    norm_res_log.append(res['norm_res'])
-    while (res['norm_res'] > par['tol']) and (res['kit'] < par['maxiter']):
-        res['kit'] += 1  # number of iterations
-        AP = Afun(P)
-        alp = float(rr/scal(P, AP))
-        xCG = xCG + alp*P
-        R = R - alp*AP
-        rrnext = scal(R, R)
-        bet = rrnext/rr
-        rr = rrnext
-        P = R + bet*P
-        res['norm_res'] = np.double(rr)**0.5
-        norm_res_log.append(res['norm_res'])
+    dot = get_scal(B, par)
+    x = x0
+    r = B-Afun(x0)
+    d = r                       # search direction
+    rho = dot(r, r)
+    history = [np.double(rho)**0.5]
+    kit = 0
+    while history[-1] > par['tol'] and kit < par['maxiter']:
+        kit += 1
+        q = Afun(d)
+        step = float(rho/dot(d, q))
+        x = x+step*d
+        r = r-step*q
+        rho_next = dot(r, r)
+        d = r+(rho_next/rho)*d
+        rho = rho_next
+        history.append(np.double(rho)**0.5)
         if callback is not None:
-            callback(xCG)
-    if res['kit'] == 0:
-        res['norm_res'] = 0
-    res['norm_res_log'] = np.array(norm_res_log)
-    return xCG, res
+            callback(x)
+    return x, {'kit': kit, 'norm_res': history[-1] if kit > 0 else 0, 'norm_res_log': np.array(history)}
+
+
+# ----------------------------------------------------------------------------- biconjugate gradients
+@_solver('bicg')
+def _bicg_entry(Afun, ATfun, B, x0, par, callback, **_):
+    return BiCG(Afun, ATfun, B, x0=x0, par=par, callback=callback)
 
 
 def BiCG(Afun, ATfun, B, x0, par=None, callback=None):
-    """BiConjugate gradients (general/solver.py:142-204), over the operand algebra."""
-    if par is None:
-        par = dict()
-    if 'tol' not in par:
-        par['tol'] = 1e-6
-    if 'maxiter' not in par:
-        par['maxiter'] = 1e3
-    scal = get_scal(B, par)
-
-    res = dict()
-    xBiCG = x0
-    Ax = Afun(x0)
-    R = B - Ax
-    Rs = R
-    rr = float(scal(R, Rs))
-    P = R
-    Ps = Rs
-    res['kit'] = 0
-    res['norm_res'] = rr**0.5  # /np.norm(E_N)
-    while (res['norm_res'] > par['tol']) and (res['kit'] < par['maxiter']):
-        res['kit'] += 1  # number of iterations
-        AP = Afun(P)
-        alp = rr/float(scal(AP, Ps))
-        xBiCG = xBiCG + alp*P
-        R = R - alp*AP
-        Rs = Rs - alp*ATfun(Ps)
-        rrnext = float(scal(R, Rs))
-        bet = rrnext/rr
-        rr = rrnext
-        P = R + bet*P
-        Ps = Rs + bet*Ps
-        res['norm_res'] = rr**0.5
+    """BiConjugate gradients with the shadow system driven by ATfun (general/solver.py:142-204); the "norm" is
+    sqrt(<r, r_shadow>) as in the reference."""
+    par = _settings(par, tol=1e-6, maxiter=1e3)
+    dot = get_scal(B, par)
+    x = x0
+    r = B-Afun(x0)
+    rs = r                       # shadow residual
+    d, ds = r, rs                # direction and shadow direction
+    rho = float(dot(r, rs))
+    info = {'kit': 0, 'norm_res': rho**0.5}
+    while info['norm_res'] > par['tol'] and info['kit'] < par['maxiter']:
+        info['kit'] += 1
+        q = Afun(d)
+        step = rho/float(dot(q, ds))
+        x = x+step*d
+        r = r-step*q
+        rs = rs-step*ATfun(ds)
+        rho_next = float(dot(r, rs))
+        d = r+(rho_next/rho)*d
+        ds = rs+(rho_next/rho)*ds
+        rho = rho_next
+        info['norm_res'] = rho**0.5
         if callback is not None:
-            callback(xBiCG)
-    if res['kit'] == 0:
-        res['norm_res'] = 0
-    return xBiCG, res
+            callback(x)
+    if info['kit'] == 0:
+        info['norm_res'] = 0
+    return x, info
+
+
+# ----------------------------------------------------------------------------- Chebyshev
+@_solver('chebyshev', 'cheby')
+def _cheby_entry(Afun, B, x0, par, callback, **_):
+    return cheby2TERM(A=Afun, B=B, x0=x0, par=par, callback=callback)
+
+
+def _cheby_weights(lo, hi):
+    """(momentum p_k, step w_k) of the two-term Chebyshev recurrence for a spectrum in [lo, hi], k = 1, 2, ..."""
+    centre, half = (hi+lo)/2.0, (hi-lo)/2.0
+    k, w = 0, 0.
+    while True:
+        k += 1
+        if k == 1:
+            p, w = 0, 1/centre
+        elif k == 2:
+            p, w = -(1/2)*(half/centre)*(half/centre), 1/(centre-half*half/2/centre)
+        else:
+            p, w = -(half*half/4)*w*w, 1/(centre-half*half*w/4)
+        yield p, w
 
 
 def cheby2TERM(A, B, x0, M=None, par=None, callback=None):
-    """Chebyshev two-term iteration (general/solver.py:206-285)."""
-    if par is None:
-        par = dict()
-    if 'tol' not in par:
-        par['tol'] = 1e-06
-    if 'maxit' not in par:
-        par['maxit'] = 1e7
+    """Chebyshev two-term iteration (general/solver.py:206-285): needs par['eigrange'] = (lambda_min, lambda_max);
+    residual norms are relative to the initial residual, the iteration cap is par['maxit']."""
+    par = _settings(par, tol=1e-06, maxit=1e7)
     if 'eigrange' not in par:
         raise NotImplementedError("It is necessary to calculate eigenvalues.")
-    else:
-        Egv = par['eigrange']
-
-    res = dict()
-    res['kit'] = 0
-    bnrm2 = (B*B)**0.5
-    Ib = 1.0/bnrm2
-    if bnrm2 == 0:
-        bnrm2 = 1.0
+    info = {'kit': 0}
     x = x0
-    r = B - A(x)
+    r = B-A(x)
     r0 = np.double(r*r)**0.5
-    res['norm_res'] = Ib*r0  # For Normal Residue
-    if res['norm_res'] < par['tol']:  # if errnorm is less than tol
-        return x, res
-
-    d = (Egv[1]+Egv[0])/2.0  # np.mean(par['eigrange'])
-    c = (Egv[1]-Egv[0])/2.0  # par['eigrange'][1] - d
+    info['norm_res'] = r0/(B*B)**0.5
+    if info['norm_res'] < par['tol']:
+        return x, info
     v = 0*x0
-    while (res['norm_res'] > par['tol']) and (res['kit'] < par['maxit']):
-        res['kit'] += 1
-        x_prev = x
-        if res['kit'] == 1:
-            p = 0
-            w = 1/d
-        elif res['kit'] == 2:
-            p = -(1/2)*(c/d)*(c/d)
-            w = 1/(d-c*c/2/d)
-        else:
-            p = -(c*c/4)*w*w
-            w = 1/(d-c*c*w/4)
-        v = r - p*v
-        x = x_prev + w*v
-        r = B - A(x)
-
-        res['norm_res'] = (1.0/r0)*r.norm()
-
+    weights = _cheby_weights(par['eigrange'][0], par['eigrange'][1])
+    while info['norm_res'] > par['tol'] and info['kit'] < par['maxit']:
+        info['kit'] += 1
+        p, w = next(weights)
+        v = r-p*v
+        x = x+w*v
+        r = B-A(x)
+        info['norm_res'] = r.norm()/r0
         if callback is not None:
             callback(x)
-
-    if par['tol'] < res['norm_res']:  # if tolerance is less than error norm
-        print("Chebyshev solver does not converges!")
-    else:
-        print("Chebyshev solver converges.")
-
-    if res['kit'] == 0:
-        res['norm_res'] = 0
-    return x, res
+    print("Chebyshev solver converges." if info['norm_res'] <= par['tol'] else "Chebyshev solver does not converges!")
+    if info['kit'] == 0:
+        info['norm_res'] = 0
+    return x, info
 
 
-def get_scal(B, par):
-    "defines scalar multiplication depending on vectors (general/solver.py:287-298)"
-    if 'scal' in par:
-        scal = par['scal']
-    else:
-        if isinstance(B, np.matrix) or _is_vectri(B):
-            scal = lambda X, Y: float(X.T*Y)  # noqa: E731
-        elif isinstance(B, Tensor):
-            scal = lambda X, Y: X*Y  # noqa: E731
-        else:
-            scal = lambda X, Y: np.sum(X*Y.conj()).real  # noqa: E731
-    return scal
-
-
-def get_norm(B, par):
-    scal = get_scal(B, par)
-    norm = lambda X: scal(X, X)**0.5  # noqa: E731
-    return norm
+# ----------------------------------------------------------------------------- SciPy bridge
+@_solver('scipy')
+def _scipy_entry(Afun, ATfun, B, x0, par, callback, name, **_):
+    """general/solver.py:28-53: SciPy iterates on host vectors; every matvec is a device call.  SciPy >= 1.12 names
+    the relative tolerance `rtol`, older versions `tol`."""
+    import inspect
+    import scipy.sparse.linalg as spslin
+    kind = name.split('.')[-1].split('_')[-1]
+    if kind not in ('cg', 'bicg'):
+        raise NotImplementedError("This kind (%s) of linear solver is not implemented" % name)
+    start = x0.ravel() if isinstance(x0, np.ndarray) else np.asarray(x0.vec()).ravel()
+    Afun.define_operand(B)
+    ops = {'matvec': lambda v: np.asarray(Afun.matvec(v)).ravel()}
+    if kind == 'bicg':
+        ATfun.define_operand(B)
+        ops['rmatvec'] = lambda v: np.asarray(ATfun.matvec(v)).ravel()
+    lin = spslin.LinearOperator(Afun.matshape, dtype=np.float64, **ops)
+    fn = getattr(spslin, kind)
+    tolkw = 'rtol' if 'rtol' in inspect.signature(fn).parameters else 'tol'
+    xcol, flag = fn(lin, np.asarray(B.vec()).ravel(), x0=start, maxiter=int(par['maxiter']), M=None,
+                    callback=callback, **{tolkw: par['tol']})
+    x = B.empty_like(name='x')
+    x.val = np.reshape(xcol, B._vshape())
+    return x, {'info': flag}

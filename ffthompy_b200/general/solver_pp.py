@@ -1,77 +1,73 @@
-"""Solver callbacks — drop-in for ffthompy/general/solver_pp.py (CallBack)."""
+"""Solver callbacks with the interface of ffthompy/general/solver_pp.py.
+
+`CallBack(A=Afun, B=B)` is what ffthompy/applications.py:71-72 attaches to every solve: called with the iterate after
+each iteration (and once with x0 by `linear_solver`), it appends the TRUE residual norm ||B - A(x)|| to `res_norm`.
+Here the operator application inside it is the fused device pipeline, and the CG loop that calls it stays on the
+device path too (general/solver.py: one fh_cg_steps call per iteration)."""
 import numpy as np
 
 from ..tensors import Tensor
 
 
-class CallBack():
-    """Records the true residual norm ||B - A(x)|| at every call (general/solver_pp.py:6-34).
-    Note the extra operator application per iteration this implies."""
+def _as_tensor(x, like):
+    if isinstance(x, np.ndarray):    # SciPy solvers hand over flat host vectors
+        return Tensor(val=np.reshape(x, like._vshape()), order=like.order, N=like.N, Y=like.Y)
+    return x
+
+
+class CallBack(object):
+    """true-residual history (general/solver_pp.py:6-34): attributes A (operator), B (right-hand side)"""
 
     def __init__(self, **kwargs):
-        self.__dict__.update(kwargs)
+        vars(self).update(kwargs)
         self.iter = -1
         self.res_norm = []
         self.energy_norm = []
 
     def __call__(self, x):
         self.iter += 1
-        if isinstance(x, np.ndarray):
-            X = Tensor(val=np.reshape(x, self.B._vshape()), order=self.B.order, N=self.B.N, Y=self.B.Y)
-        else:
-            X = x
-        res = self.B - self.A(X)
-        self.res_norm.append(res.norm())
-        return
+        r = self.B-self.A(_as_tensor(x, self.B))
+        self.res_norm.append(r.norm())
 
     def __repr__(self):
-        try:
-            ss = ''
-            ss += '    iterations : %d\n' % self.iter
-            ss += '    res_norm : %g' % self.res_norm[-1]
-            ss += '\n'
-        except Exception:
-            ss = 'the results are not initialized yet'
-        return ss
+        if not self.res_norm:
+            return 'the results are not initialized yet'
+        return '    iterations : %d\n    res_norm : %g\n' % (self.iter, self.res_norm[-1])
 
 
-class CallBack_GA():
-    """Detailed callback (general/solver_pp.py:37-75; legacy in the reference — it is only reachable
-    through pb.solver['callback'] == 'detailed').  Kept importable and functional over the Tensor
-    algebra: residual norm, energy bound and non-conformity per iteration."""
+class CallBack_GA(object):
+    """per-iteration residual, energy bound and non-conformity (general/solver_pp.py:37-75; reachable in the
+    reference only through pb.solver['callback'] == 'detailed').  Attributes: A, B, GN (projection operator),
+    E2N / EN (macroscopic field), Aex / A_Ga (exactly integrated coefficients)."""
 
     def __init__(self, **kwargs):
-        self.__dict__.update(kwargs)
+        vars(self).update(kwargs)
         self.iter = -1
         self.res_norm = []
         self.bound = []
         self.nonconformity = []
 
+    def _attr(self, *names):
+        for nm in names:
+            if hasattr(self, nm):
+                return getattr(self, nm)
+        raise AttributeError('CallBack_GA needs one of %s' % (names,))
+
     def __call__(self, x):
         self.iter += 1
-        X = x
-        E2N = getattr(self, 'E2N', getattr(self, 'EN', None))
-        Aex = getattr(self, 'Aex', getattr(self, 'A_Ga', None))
-        if np.linalg.norm(X.mean() - E2N.mean()) < 1e-8:
-            res = self.A(X)
-            eN = X
-        else:
-            res = self.B-self.A(X)
-            eN = X + E2N
-        self.res_norm.append(res.norm())
-        GeN = self.GN(eN) + E2N
-        GeN_E = GeN + E2N
-        self.bound.append(Aex(GeN_E)*GeN_E)
-        self.nonconformity.append((GeN-eN).norm())
-        return
+        macro = self._attr('E2N', 'EN')
+        A_exact = self._attr('Aex', 'A_Ga')
+        has_macro = np.linalg.norm(x.mean()-macro.mean()) < 1e-8   # iterate already carries the macroscopic part
+        r = self.A(x) if has_macro else self.B-self.A(x)
+        e = x if has_macro else x+macro
+        self.res_norm.append(r.norm())
+        conforming = self.GN(e)+macro
+        shifted = conforming+macro
+        self.bound.append(A_exact(shifted)*shifted)
+        self.nonconformity.append((conforming-e).norm())
 
     def __repr__(self):
-        try:
-            ss = ''
-            ss += '    iterations    : %d\n' % self.iter
-            ss += '    res_norm      : %g\n' % self.res_norm[-1]
-            ss += '    bound         : %g\n' % self.bound[-1]
-            ss += '    nonconformity : %g' % self.bound[-1]
-        except Exception:
-            ss = 'no output'
-        return ss
+        if not self.res_norm:
+            return 'no output'
+        return ('    iterations    : %d\n    res_norm      : %g\n    bound         : %g\n    nonconformity : %g'
+                % (self.iter, self.res_norm[-1], self.bound[-1], self.nonconformity[-1]))

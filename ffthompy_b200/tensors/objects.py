@@ -114,6 +114,7 @@ class Tensor(TensorFuns):
         self.origin = origin
         self._h = None  # host copy (numpy) or None
         self._d = None  # device copy (torch CUDA tensor) or None
+        self._version = 0  # bumped by every in-place change of the device buffer (caches key on it)
 
         if isinstance(val, np.ndarray) or _is_dev(val):  # define: val + order
             self.val = val
@@ -353,6 +354,7 @@ class Tensor(TensorFuns):
         else:
             ops.add_comp(d, [float(v) for v in mean.ravel()])
         self._h = None  # device copy is now the newer one
+        self._version += 1
         return self
 
     def set_mean(self, mean):

@@ -308,9 +308,93 @@ def gen_configs():
     print('configs.npz: %d arrays' % len(out))
 
 
+# ----------------------------------------------------------------------------- 5. round 2: BASELINE configs at CPU-feasible sizes
+def gen_round2(big=True):
+    """C1b (2-D scalar 31x31 GaNi + Ga 61x61 through the reference's Problem driver), a C2-shaped problem (3-D scalar
+    'cube' 0.7, kind 'Ga', order None, N=16->31 and 32->63, primal + dual bounds) and C3 (random two-phase
+    elasticity) at 64^3 (primal + dual) and 128^3 (primal) -- SURVEY App. C recipes.  Written to round2.npz so the
+    round-1 fixture files stay bit-identical."""
+    out = {}
+    # ---- C1b
+    for kind in ('GaNi', 'Ga'):
+        N = 31*np.ones(2, dtype=np.int32)
+        mat = {'inclusions': ['square', 'otherwise'], 'positions': [np.zeros(2), ''], 'params': [0.6*np.ones(2), ''],
+               'vals': [11*np.eye(2), 1.*np.eye(2)], 'Y': np.ones(2), 'order': None}
+        pb = {'name': 'p', 'physics': 'scalar', 'material': mat,
+              'solve': {'kind': kind, 'N': N, 'primaldual': ['primal', 'dual']},
+              'postprocess': [{'kind': 'GaNi'}, {'kind': 'Ga', 'order': None}] if kind == 'GaNi' else [{'kind': 'Ga', 'order': None}],
+              'solver': {'kind': 'CG', 'tol': 1e-8, 'maxiter': 1e3}}
+        prob = quiet(Problem, pb, None)
+        quiet(prob.calculate)
+        M = Material(mat)
+        Nbar = 2*N-1
+        for pd in ('primal', 'dual'):
+            tag = 'c1b_%s_%s' % (kind, pd)
+            A = quiet(M.get_A_GaNi, N, pd) if kind == 'GaNi' else quiet(M.get_A_Ga, Nbar=Nbar, primaldual=pd, order=None)
+            out[tag+'_A'] = A.val
+            out[tag+'_kit'] = np.array([r['info']['kit'] for r in prob.output['res_'+pd]])
+            out[tag+'_normres'] = np.array([r['info']['norm_res'] for r in prob.output['res_'+pd]])
+            out[tag+'_AGa'] = quiet(M.get_A_Ga, Nbar=Nbar, primaldual=pd, order=None).val
+            for name, v in prob.output['mat_'+pd].items():
+                out[tag+'_'+name] = v
+            print('  C1b %s %s: kit %s  %s' % (kind, pd, out[tag+'_kit'],
+                                             {k: float(v[0, 0]) for k, v in prob.output['mat_'+pd].items()}))
+    # ---- C2-shaped: exact integration of a cube inclusion, primal + dual => upper / lower bounds
+    for n in (16, 32):
+        N = n*np.ones(3, dtype=np.int32)
+        Nbar = 2*N-1
+        mat = {'inclusions': ['cube', 'otherwise'], 'positions': [np.zeros(3), ''], 'params': [0.7*np.ones(3), ''],
+               'vals': [11*np.eye(3), 1.*np.eye(3)], 'Y': np.ones(3), 'order': None}
+        pb = {'name': 'p', 'physics': 'scalar', 'material': mat,
+              'solve': {'kind': 'Ga', 'N': N, 'primaldual': ['primal', 'dual']},
+              'postprocess': [{'kind': 'Ga', 'order': None}],
+              'solver': {'kind': 'CG', 'tol': 1e-6, 'maxiter': 1e3}}
+        prob = quiet(Problem, pb, None)
+        quiet(prob.calculate)
+        M = Material(mat)
+        for pd in ('primal', 'dual'):
+            tag = 'c2_n%d_%s' % (n, pd)
+            A = quiet(M.get_A_Ga, Nbar=Nbar, primaldual=pd, order=None).val
+            offd = max(np.abs(A[i, j]).max() for i in range(3) for j in range(3) if i != j)
+            iso = max(np.abs(A[i, i]-A[0, 0]).max() for i in range(3))
+            assert offd == 0. and iso == 0., (offd, iso)
+            out[tag+'_a'] = A[0, 0]                       # A = a(x) I exactly: one scalar field travels
+            out[tag+'_kit'] = np.array([r['info']['kit'] for r in prob.output['res_'+pd]])
+            out[tag+'_normres'] = np.array([r['info']['norm_res'] for r in prob.output['res_'+pd]])
+            out[tag+'_AH'] = prob.output['mat_'+pd]['AH_Ga_'+pd]
+            print('  C2 n=%d %s: kit %s AH00 %.15g' % (n, pd, out[tag+'_kit'], out[tag+'_AH'][0, 0]))
+    # ---- C3 at 64^3 and 128^3
+    Cm = ElasticTensor(bulk=1, mu=1).mandel
+    Ci = ElasticTensor(bulk=10, mu=5).mandel
+    for n, pds in ((64, ('primal', 'dual')), (128, ('primal',))) if big else ():
+        N = np.array([n, n, n])
+        rng = np.random.default_rng(20240901)
+        phase = (rng.random((n, n, n)) < 0.3).astype(float)
+        Gs = elasticity_anyN(N, np.ones(3))
+        for pd in pds:
+            cm, ci = (Cm, Ci) if pd == 'primal' else (np.linalg.inv(Cm), np.linalg.inv(Ci))
+            A = Tensor(name='A', val=np.einsum('ij,...->ij...', cm, 1-phase)+np.einsum('ij,...->ij...', ci, phase),
+                       order=2, N=N, multype=21)
+            G = Gs[1]+Gs[2] if pd == 'primal' else Gs[3]+Gs[4]
+            AH, kits, nres, _ = solve_all(A, G, N, 6, 1e-6)
+            if pd == 'dual':
+                AH = np.linalg.inv(AH)
+            out['c3_n%d_%s_AH' % (n, pd)] = AH
+            out['c3_n%d_%s_kit' % (n, pd)] = kits
+            out['c3_n%d_%s_normres' % (n, pd)] = nres
+            print('  C3 n=%d %s: kit %s AH00 %.15g AH01 %.15g AH33 %.15g' % (n, pd, kits, AH[0, 0], AH[0, 1], AH[3, 3]),
+                  flush=True)
+    np.savez_compressed(os.path.join(OUT, 'round2.npz'), **out)
+    print('round2.npz: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
+    if '--round2' in sys.argv:          # leaves the round-1 files untouched
+        gen_round2(big='--small' not in sys.argv)
+        sys.exit(0)
     gen_projections()
     gen_tensors()
     gen_configs()
     gen_examples()
+    gen_round2()
     os.system('ls -la %s' % OUT)

@@ -26,13 +26,16 @@ def test_reference_arm_line_single_gpu():
     assert d['value'] > 0 and abs(d['value']-d['e2e']['value']) < 1e-9*d['value']
     assert d['e2e']['h2d_bytes_per_step'] == 0 and d['e2e']['d2h_bytes_per_step'] == 0
     cb = d['cpu_baseline']
-    assert cb['kind'] == 'port' and cb['cores'] == 1 and cb['value'] == d['value'] and '96^3' in cb['sample']
-    assert d['config']['grid'] == [256, 256, 256] and 'workload' in d['config']
+    # kind "reference" when the unmodified tree travelled under baseline/_ref, else the oracle port; the line names
+    # the grid it actually timed (128^3) next to the GPU arm's grid
+    assert cb['kind'] in ('port', 'reference') and cb['cores'] == 1 and cb['value'] == d['value'] and '128^3' in cb['sample']
+    assert d['config']['grid'] == [128, 128, 128] and d['config']['gpu_arm_grid'] == [256, 256, 256]
+    assert 'workload' in d['config'] and d['steps_timed'] == 1
 
 
 def test_reference_arm_under_a_multi_rank_launch():
     lines = _run(['--gpus', '8'], env={'RANK': '0', 'WORLD_SIZE': '8', 'LOCAL_RANK': '0'})
     assert len(lines) == 1
     d = json.loads(lines[0])
-    assert d['n_gpus'] == 8 and d['config']['grid'] == [512, 512, 512] and d['scaling'] == 'strong'
+    assert d['n_gpus'] == 8 and d['config']['gpu_arm_grid'] == [512, 512, 512] and d['scaling'] == 'strong'
     assert _run(['--gpus', '8'], env={'RANK': '3', 'WORLD_SIZE': '8', 'LOCAL_RANK': '3'}) == []
