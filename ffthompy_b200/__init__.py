@@ -26,13 +26,14 @@ def install(reference_package='ffthompy'):
     Call before importing the reference's callers."""
     import importlib
     ref = importlib.import_module(reference_package)  # the reference tree must be importable
-    from . import tensors, projections, trigpol
+    from . import tensors, projections, trigpol, postprocess
     from .tensors import objects, operators, projection, fft
     from .general import solver, solver_pp
     mapping = {
         'tensors': tensors, 'tensors.objects': objects, 'tensors.operators': operators,
         'tensors.projection': projection, 'tensors.fft': fft, 'projections': projections,
         'general.solver': solver, 'general.solver_pp': solver_pp, 'trigpol': trigpol,
+        'postprocess': postprocess,
     }
     for name, mod in mapping.items():
         sys.modules[reference_package+'.'+name] = mod

@@ -61,6 +61,7 @@ _SIGNATURES = {
     'fh_hadamard': (c_int, [c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp, c_int, c_vp]),
     'fh_contract_first': (c_int, [c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'fh_inv_dxd': (c_int, [c_int, c_i64, c_vp, c_vp]),
+    'fh_assemble_AH': (c_int, [c_int, c_int, c_i64, c_vp, C.POINTER(c_vp), p_dbl]),
     'fh_spec_remap': (c_int, [c_int, p_i64, c_int, p_i64, c_int, c_i64, c_dbl, c_int, c_vp, c_vp]),
     'fh_roll': (c_int, [c_int, p_i64, p_i64, c_int, c_i64, c_vp, c_vp]),
     'fh_grad': (c_int, [c_int, p_i64, p_dbl, c_int, c_int, c_vp, c_vp]),

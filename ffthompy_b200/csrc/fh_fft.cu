@@ -41,6 +41,12 @@ extern "C" int fh_init(int device) {
     g_num_sms = prop.multiProcessorCount;
     g_smem_optin = (int)prop.sharedMemPerBlockOptin;
     g_device = device;
+    // L2 fill granularity (FH_L2FETCH = 32 | 64 | 128 bytes; unset: driver default).  The axis-0 pass reads 64-byte
+    // row segments whose other half belongs to the neighbouring tile; with 128-byte fills the second reader hits L2.
+    const char* fg = getenv("FH_L2FETCH");
+    if (fg && atoi(fg) > 0) {
+        FH_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)));
+    }
     return FH_OK;
 }
 

@@ -10,7 +10,7 @@ static int mid2_env(const char* name, int dflt) {
 }
 bool fh_mid2_len(int n) {
     static const int on = mid2_env("FH_MID2", 1);
-    return on && (n == 64 || n == 128 || n == 256);
+    return on && (n == 128 || n == 256);  // (64 keeps the round-1 kernel: 64 threads per CTA would leave the SM idle)
 }
 
 template <int N, int KIND, int MINB, int PREF>
@@ -61,7 +61,6 @@ int fh_mid2_green(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& 
     m.col0 = col0;
     const bool el = kind == FH_GREEN_ELASTIC;
     switch (N) {
-        case 64: return el ? mid2_N<64, FH_GREEN_ELASTIC>(data, tw, g, m, nh) : mid2_N<64, FH_GREEN_SCALAR>(data, tw, g, m, nh);
         case 128: return el ? mid2_N<128, FH_GREEN_ELASTIC>(data, tw, g, m, nh) : mid2_N<128, FH_GREEN_SCALAR>(data, tw, g, m, nh);
         case 256: return el ? mid2_N<256, FH_GREEN_ELASTIC>(data, tw, g, m, nh) : mid2_N<256, FH_GREEN_SCALAR>(data, tw, g, m, nh);
     }

@@ -1045,6 +1045,74 @@ extern "C" int fh_cg_xr_update(int64_t n, double* x, double* r, const double* p,
     FH_LAUNCH_CHECK();
     return finish_reduction((int)g, 1, 0, rr_local_host);
 }
+// ------------------------------------------------------------------ homogenised matrix in one pass (K10)
+// AH[s][s2] = sum_v (A e_s)(v) . e_s2(v)   for the NS minimisers e_s (D components each): the coefficient array is read
+// ONCE per voxel for all NS*NS entries (ffthompy/postprocess.py:53-70 evaluates Afun(sol[ii]) * sol[jj] for every
+// pair, i.e. NS*NS matrix-vector passes over A).  Per-CTA partial sums [NS*NS][gridDim], fixed-order final reduction.
+struct SolPtrs {
+    const double* p[6];
+};
+template <int D, int NS>
+__global__ void __launch_bounds__(FH_NT) k_assemble_AH(int64_t n, const double* __restrict__ A, SolPtrs sol,
+                                                       double* __restrict__ part) {
+    __shared__ double red[32];
+    double acc[NS][NS];
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) acc[a][b] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+        double e[NS][D];
+#pragma unroll
+        for (int a = 0; a < NS; ++a)
+#pragma unroll
+            for (int j = 0; j < D; ++j) e[a][j] = sol.p[a][(size_t)j * n + v];
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            double row[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) row[j] = A[((size_t)i * D + j) * n + v];
+#pragma unroll
+            for (int a = 0; a < NS; ++a) {
+                double t = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) t += row[j] * e[a][j];
+#pragma unroll
+                for (int b = 0; b < NS; ++b) acc[a][b] += t * e[b][i];
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < NS; ++a)
+#pragma unroll
+        for (int b = 0; b < NS; ++b) {
+            const double r = block_sum(acc[a][b], red);
+            if (threadIdx.x == 0) part[(size_t)(a * NS + b) * gridDim.x + blockIdx.x] = r;
+        }
+}
+// A: [D][D][n] real coefficients; sols_host: nsol DEVICE pointers to real fields [D][n]; AH_host: nsol*nsol sums
+// (not normalised: the caller divides by prod(N), tensors/objects.py:635).  nsol == D in {2, 3, 6}.
+extern "C" int fh_assemble_AH(int D, int nsol, int64_t n, const double* A, const double* const* sols_host,
+                              double* AH_host) {
+    FH_REQUIRE(A && sols_host && AH_host && n > 0, "fh_assemble_AH: bad argument");
+    FH_REQUIRE(nsol == D && (D == 2 || D == 3 || D == 6), "fh_assemble_AH: D = nsol in {2, 3, 6} (got %d, %d)", D, nsol);
+    int rc;
+    if ((rc = ensure_scratch())) return rc;
+    SolPtrs sp;
+    for (int a = 0; a < 6; ++a) sp.p[a] = (a < nsol) ? sols_host[a] : NULL;
+    for (int a = 0; a < nsol; ++a) FH_REQUIRE(sp.p[a], "fh_assemble_AH: null solution pointer %d", a);
+    unsigned g = grid_for(n, 1);
+    if (g > 1024) g = 1024;
+    switch (D) {
+        case 2: k_assemble_AH<2, 2><<<g, FH_NT, 0, fh_stream()>>>(n, A, sp, g_red_dev); break;
+        case 3: k_assemble_AH<3, 3><<<g, FH_NT, 0, fh_stream()>>>(n, A, sp, g_red_dev); break;
+        case 6: k_assemble_AH<6, 6><<<g, FH_NT, 0, fh_stream()>>>(n, A, sp, g_red_dev); break;
+    }
+    FH_LAUNCH_CHECK();
+    return finish_reduction((int)g, nsol * nsol, 0, AH_host);
+}
+
 // p = r + beta p   (solver.py:132)
 __global__ void k_p_update(int64_t n, double* __restrict__ p, const double* __restrict__ r, double beta) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;

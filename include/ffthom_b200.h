@@ -98,6 +98,10 @@ int fh_hadamard(int64_t n, int nc, int adiv, int ca, int bdiv, int cb, const dou
 int fh_contract_first(int64_t n, int d, int K, const double* a, const double* b, double* out);
 /* Gauss-Jordan inverse per voxel (ffthompy/trigpol.py:120-159) */
 int fh_inv_dxd(int D, int64_t n, const double* A, double* Ainv);
+/* homogenised matrix in one pass over the coefficients (ffthompy/postprocess.py:53-70: AH[i][j] = Afun(sol[i]) * sol[j]
+ * for every pair): A [D][D][n] real, sols_host = nsol DEVICE pointers to the minimisers [D][n] (nsol == D in {2,3,6});
+ * AH_host[i*nsol+j] = sum over voxels of (A e_i).e_j, NOT divided by prod(N) */
+int fh_assemble_AH(int D, int nsol, int64_t n, const double* A, const double* const* sols_host, double* AH_host);
 
 /* ---- spectra: form changes, enlarge/decrease, shifts (tensors/objects.py:135-186,428-486;
  *      trigpol.py:162-214) ----------------------------------------------------------- */
@@ -132,6 +136,8 @@ int64_t fh_ga_slab_work_doubles(const fh_plan* plan, int D, int n0_local, int n1
 int fh_ga_create_slab(fh_ga** op, const fh_plan* plan, int D, const double* A_local, int a_layout, const fh_green* g,
                       double* work, int n0_local, int n1_local, int n1_offset);
 int fh_ga_buffers(const fh_ga* op, void** spec, void** specT, int* pitch);
+/* (bufA / bufB below must be handed in ZERO-FILLED: the padding columns travel with the rows, and the library writes
+ * nothing into peer-mapped buffers outside the stages) */
 /* Zero-copy, chunked slab pipeline (SURVEY §8e "overlap the all-to-all with the local FFT passes"):
  * bufA / bufB are caller-owned exchange buffers of D*n0_local*N1*pitch complex128 each, organised as
  * nchunk contiguous blocks [world][D][n0_local/nchunk][n1_local][pitch]; the axis-1 and axis-0 kernels
