@@ -680,12 +680,14 @@ def run_slab(args):
     F = 8.*D*nvox/world
     Fs = 16.*D*lay.n0l*n*P
     alg = {1: F+1.*nvox/world+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
-    names = {1: 'S1 A.p + R2C (last axis)', 2: 'S2 C2C axis 1',
-             3: 'S3 C2C axis 0 + Green + inverse axis 0, fused with the exchange (remote loads/stores over NVLink)'
-                if op.mode == 'peer' else 'S3 C2C axis 0 + Green + inverse axis 0',
+    names = {1: 'S1 A.p + R2C (last axis)',
+             2: 'S2 C2C axis 1, rows stored into the owners y-slab spectra over NVLink' if op.mode == 'push' else 'S2 C2C axis 1',
+             3: {'peer': 'S3 C2C axis 0 + Green + inverse axis 0, fused with the exchange (remote loads/stores over NVLink)',
+                 'push': 'S3 C2C axis 0 + Green + inverse axis 0, rows stored into the owners x-slab spectra over NVLink'
+                 }.get(op.mode, 'S3 C2C axis 0 + Green + inverse axis 0'),
              4: 'S4 inverse C2C axis 1', 5: 'S5 C2R (last axis) + <p,Ap>'}
     stage_ms = {}
-    if op.mode in ('peer', 'packed'):
+    if op.mode in ('peer', 'push', 'packed'):
         xin = dev.zeros(shape)
         xin.normal_()
         y = dev.zeros(shape)

@@ -79,6 +79,8 @@ _SIGNATURES = {
     'fh_ga_last_dot': (c_int, [c_vp, p_dbl]),
     'fh_ga_slab_direct': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     'fh_ga_slab_peer': (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp)]),
+    'fh_ga_slab_push': (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    'fh_ga_slab_push_stage': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'fh_ga_slab_stage': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'fh_cgd_init': (c_int, [c_vp, c_vp, c_vp]),
     'fh_cgd_update': (c_int, [c_vp, c_vp, c_vp]),

@@ -997,6 +997,7 @@ extern "C" int fh_ga_destroy(fh_ga* op) {
     if (op->phase) cudaFree(op->phase);
     if (op->lut) cudaFree(op->lut);
     if (op->sd_off1) cudaFree(op->sd_off1);
+    if (op->sp_off1) cudaFree(op->sp_off1);
     cudaFree(op->scal);
     cudaFreeHost(op->pinned);
     free(op);
@@ -1455,6 +1456,16 @@ static int launch_mid_map(fh_ga* op) {
         case 2048: return launch_mid_map_NT<2048, 1, KIND>(op);
     }
     return fh_set_error(FH_ERR_UNSUPPORTED, "no slab-exchange kernel for N0=%d", op->plan->N[0]);
+}
+
+int fh_launch_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo, int64_t panels,
+                      int pitch, bool inv) {
+    return launch_c2c_map(N, tw, in, out, mi, mo, panels, pitch, inv);
+}
+int fh_ga_stage_local(fh_ga* op, int stage, double* x, const double* r, int pupdate, double* y, int dot, int* npart) {
+    const int rc = ga_stage(op, stage, x, r, pupdate, y, dot, npart);
+    if (stage == 5 && !rc && npart) op->last_npart = *npart;
+    return rc;
 }
 
 extern "C" int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, void* bufB) {

@@ -56,5 +56,14 @@ struct fh_ga {
     int64_t* sd_off0;   // [N0] row offsets of the axis-0 pass inside bufB
     int64_t sd_cs0;     // component stride of the axis-0 pass
     int sd_peer;        // 1: the axis-0 pass reads/writes the peers' x-slab spectra directly (fh_ga_slab_peer)
+    // push-mode slab exchange (fh_slab2.cu): S2 stores into the peers' y-slab spectra, S3 into their x-slab spectra
+    int sp_world;       // 0: off
+    int64_t* sp_off1;   // device [N1]: S2 output row k1 -> element offset from this rank's specT (peer-mapped memory)
+    int64_t* sp_off0;   // device [N0]: S3 output row i0 -> element offset from this rank's spec
 };
+
+// internals of fh_fused.cu used by fh_slab2.cu
+int fh_ga_stage_local(fh_ga* op, int stage, double* x, const double* r, int pupdate, double* y, int dot, int* npart);
+int fh_launch_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo, int64_t panels,
+                      int pitch, bool inv);
 

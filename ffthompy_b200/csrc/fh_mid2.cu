@@ -8,8 +8,9 @@ static int mid2_env(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
 }
+bool fh_mid2_can(int n) { return n == 128 || n == 256; }
 bool fh_mid2_len(int n) {
-    static const int on = mid2_env("FH_MID2", 1);
+    static const int on = mid2_env("FH_MID2", 0);  // opt-in: measured slower than k_mid_green_pipe
     return on && (n == 128 || n == 256);  // (64 keeps the round-1 kernel: 64 threads per CTA would leave the SM idle)
 }
 
@@ -46,7 +47,8 @@ static int mid2_N(cplx* data, const cplx* tw, const GreenDesc& g, const Mid2Map&
 }
 
 int fh_mid2_green(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, const int64_t* rowoff,
-                  int64_t rstride, int64_t cstride, int spitch, int kcol0, int nh, int nrow, int col0, int ncols) {
+                  int64_t rstride, int64_t cstride, int spitch, int kcol0, int nh, int nrow, int col0, int ncols,
+                  cplx* dout, const int64_t* rowoff_out, int64_t cstride_out) {
     if (spitch % 8 || col0 % 8 || ncols % 8 || ncols <= 0)
         return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: 8-column tiles need 128-byte aligned rows (pitch %d, columns %d+%d)",
                             spitch, col0, ncols);
@@ -59,6 +61,9 @@ int fh_mid2_green(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& 
     m.tpr = ncols / 8;
     m.ntiles = nrow * m.tpr;
     m.col0 = col0;
+    m.dout = dout;
+    m.rowoff_out = rowoff_out;
+    m.cstride_out = cstride_out;
     const bool el = kind == FH_GREEN_ELASTIC;
     switch (N) {
         case 128: return el ? mid2_N<128, FH_GREEN_ELASTIC>(data, tw, g, m, nh) : mid2_N<128, FH_GREEN_SCALAR>(data, tw, g, m, nh);

@@ -97,6 +97,10 @@ struct Mid2Map {
     int64_t rstride, cstride;
     int spitch, kcol0;
     int ntiles, tpr, col0;  // tiles walk tpr 8-column tiles per buffer row starting at buffer column col0
+    // push mode of the slab pipeline (fh_slab2.cu): results of row i0 go to dout[c*cstride_out + rowoff_out[i0] + ii]
+    cplx* dout;
+    const int64_t* rowoff_out;
+    int64_t cstride_out;
 };
 
 template <int N, int KIND>
@@ -257,9 +261,15 @@ __global__ void __launch_bounds__((Mid2Cfg<N, KIND>::NT), MINB)
                     u[qq] = cmul(u[qq], make_double2(wq.x, -wq.y));
                 }
                 Bfly<RA, true>::run(u);
-                cplx* gp = data + (int64_t)c * m.cstride + ii + t;
+                if (m.dout) {
+                    cplx* gq = m.dout + (int64_t)c * m.cstride_out + ii + t;
 #pragma unroll
-                for (int r = 0; r < RA; ++r) gp[row_off(j + 16 * r)] = u[r];
+                    for (int r = 0; r < RA; ++r) gq[m.rowoff_out[j + 16 * r]] = u[r];
+                } else {
+                    cplx* gp = data + (int64_t)c * m.cstride + ii + t;
+#pragma unroll
+                    for (int r = 0; r < RA; ++r) gp[row_off(j + 16 * r)] = u[r];
+                }
             }
         }
         __syncthreads();  // the next F1 writes slots that the partner task (j +- 8) of the same (c, t) reads in I1

@@ -565,6 +565,26 @@ __global__ void k_spec_remap(RemapDesc d, int64_t nout, int64_t nin, int batch, 
             for (int b = 0; b < batch; ++b) out[(size_t)b * nout + o] = make_double2(0.0, 0.0);
             continue;
         }
+        // Nyquist planes of even source axes: Tensor.enlarge (tensors/objects.py:441-453) splits them axis by axis,
+        // new(-N/2) = old(-N/2)/2 and new(+N/2, k') = conj(old(-N/2, -k'))/2, where -k' flips every other axis and keeps
+        // the Nyquist index of an even axis that has not been split yet.  For spectra of real fields this is the
+        // symmetric halving; for iterates that are NOT Hermitian-consistent (grad of an even-grid Nyquist mode inside the
+        // potential-formulation CG) only this exact order reproduces the reference.  Peel the axes in reverse order:
+        bool cjn = false;
+        if (!(d.pure_pad & 1)) {
+            for (int a = dim - 1; a >= 0; --a) {
+                const int N = d.N[a];
+                if (d.M[a] > N && (N % 2 == 0) && 2 * k[a] == N) {
+                    cjn = !cjn;
+                    k[a] = -N / 2;
+                    for (int c = 0; c < dim; ++c) {
+                        if (c == a) continue;
+                        if (c > a && (d.N[c] % 2 == 0) && 2 * k[c] == -d.N[c]) continue;
+                        k[c] = -k[c];
+                    }
+                }
+            }
+        }
         // source storage index
         bool conj = false;
         if (d.fin == 1) {
@@ -602,6 +622,7 @@ __global__ void k_spec_remap(RemapDesc d, int64_t nout, int64_t nin, int batch, 
                 const cplx u = in[(size_t)b * nin + src2];
                 v = make_double2(0.5 * (v.x + u.x), 0.5 * (v.y - u.y));
             }
+            if (cjn) v.y = -v.y;
             out[(size_t)b * nout + o] = make_double2(v.x * w, v.y * w);
         }
     }

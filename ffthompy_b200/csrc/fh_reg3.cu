@@ -73,16 +73,26 @@ int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
 
 template <int N, int T, int KIND, int DIM>
 static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
-                  const int64_t* rowoff = nullptr, int64_t cstride = 0) {
+                  const int64_t* rowoff = nullptr, int64_t cstride = 0, cplx* dout = nullptr,
+                  const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int NT = 768;
     const size_t smem = (size_t)D * (N + N / 8) * T * sizeof(cplx);
     int rc;
     if ((rc = reg3_smem_attr(k_mid_green_reg3<N, T, KIND, DIM, NT>, smem))) return rc;
     k_mid_green_reg3<N, T, KIND, DIM, NT><<<(unsigned)(inner / T), NT, smem, fh_stream()>>>(
-        data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner);
+        data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner, dout, rowoff_out, cstride_out);
     FH_LAUNCH_CHECK();
     return FH_OK;
+}
+// push mode (fh_slab2.cu): natural y-slab input `data`, output rows scattered through rowoff_out into `dout`
+int fh_reg3_mid_green_push(int N, int kind, cplx* data, cplx* dout, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                           int pitch, const int64_t* rowoff_out, int64_t cstride_out) {
+    if (N != 512 || inner % 4 != 0)
+        return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass axis-0 push kernel for N0=%d inner=%lld", N, (long long)inner);
+    if (kind == FH_GREEN_SCALAR)
+        return mid_KD<512, 4, FH_GREEN_SCALAR, 3>(data, tw, g, inner, nh, pitch, nullptr, 0, dout, rowoff_out, cstride_out);
+    return mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, nullptr, 0, dout, rowoff_out, cstride_out);
 }
 int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
                       int pitch) {
@@ -114,26 +124,27 @@ int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const Gre
 }
 template <int N, int T>
 static int c2c_map_NT(const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo, int64_t panels,
-                      int pitch, bool inv) {
+                      int pitch, bool inv, int max_ctas) {
     const size_t smem = (size_t)N * T * sizeof(cplx);
     const int ntile = pitch / T;
-    const unsigned nblk = (unsigned)(panels * ntile);
+    const int64_t nwork = panels * ntile;
+    const unsigned nblk = (unsigned)((max_ctas > 0 && max_ctas < nwork) ? max_ctas : nwork);
     const int nt = T * Reg3Cfg<N>::TPL;
     int rc;
     if (inv) {
         if ((rc = reg3_smem_attr(k_c2c_reg3_map<N, T, true>, smem))) return rc;
-        k_c2c_reg3_map<N, T, true><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+        k_c2c_reg3_map<N, T, true><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile, nwork);
     } else {
         if ((rc = reg3_smem_attr(k_c2c_reg3_map<N, T, false>, smem))) return rc;
-        k_c2c_reg3_map<N, T, false><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile);
+        k_c2c_reg3_map<N, T, false><<<nblk, nt, smem, fh_stream()>>>(in, out, tw, mi, mo, ntile, nwork);
     }
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
 int fh_reg3_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
-                    int64_t panels, int pitch, bool inv) {
+                    int64_t panels, int pitch, bool inv, int max_ctas) {
     if (pitch % 8) return fh_set_error(FH_ERR_UNSUPPORTED, "three-pass exchange kernel: pitch %d", pitch);
-    if (N == 512) return c2c_map_NT<512, 8>(tw, in, out, mi, mo, panels, pitch, inv);
-    if (N == 256) return c2c_map_NT<256, 8>(tw, in, out, mi, mo, panels, pitch, inv);
+    if (N == 512) return c2c_map_NT<512, 8>(tw, in, out, mi, mo, panels, pitch, inv, max_ctas);
+    if (N == 256) return c2c_map_NT<256, 8>(tw, in, out, mi, mo, panels, pitch, inv, max_ctas);
     return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass exchange kernel for N1=%d", N);
 }

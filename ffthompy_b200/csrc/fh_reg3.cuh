@@ -274,7 +274,9 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
 template <int N, int T, int KIND, int DIM, int NT>
 __global__ void __launch_bounds__(NT, 1)
     k_mid_green_reg3(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
-                     int pitch, const int64_t* __restrict__ rowoff, int64_t cstride) {
+                     int pitch, const int64_t* __restrict__ rowoff, int64_t cstride,
+                     cplx* __restrict__ dout = nullptr, const int64_t* __restrict__ rowoff_out = nullptr,
+                     int64_t cstride_out = 0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
     constexpr int B1 = Reg3Cfg<N>::B1, B2 = Reg3Cfg<N>::B2, B3 = Reg3Cfg<N>::B3;
@@ -398,9 +400,15 @@ __global__ void __launch_bounds__(NT, 1)
 #pragma unroll
         for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, true));
         Bfly<R1, true>::run(v);
-        cplx* gp = data + (int64_t)c * cstride + i0 + t;
+        if (dout) {  // push mode of the slab pipeline: results go to the x-slab spectra of the ranks that own the planes
+            cplx* gq = dout + (int64_t)c * cstride_out + i0 + t;
 #pragma unroll
-        for (int r = 0; r < R1; ++r) gp[rowoff ? rowoff[u + r * M] : (int64_t)(u + r * M) * inner] = v[r];
+            for (int r = 0; r < R1; ++r) gq[rowoff_out[u + r * M]] = v[r];
+        } else {
+            cplx* gp = data + (int64_t)c * cstride + i0 + t;
+#pragma unroll
+            for (int r = 0; r < R1; ++r) gp[rowoff ? rowoff[u + r * M] : (int64_t)(u + r * M) * inner] = v[r];
+        }
     }
 }
 
@@ -409,48 +417,53 @@ __global__ void __launch_bounds__(NT, 1)
 template <int N, int T, bool INV>
 __global__ void __launch_bounds__(T* Reg3Cfg<N>::TPL) k_c2c_reg3_map(const cplx* __restrict__ in, cplx* __restrict__ out,
                                                                       const cplx* __restrict__ tw, LineMap mi, LineMap mo,
-                                                                      int ntile) {
+                                                                      int ntile, int64_t nwork) {
     constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
     constexpr int M = N / R1;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     cplx* smc = reinterpret_cast<cplx*>(fh_smem_raw);  // [N][T]
     const int t = threadIdx.x % T, u = threadIdx.x / T;
-    const int64_t o = blockIdx.x / ntile;
-    const int tile = blockIdx.x - (int)(o * ntile);
-    const int64_t bi = linemap_base(mi, o) + (int64_t)tile * T + t;
-    const int64_t bo = linemap_base(mo, o) + (int64_t)tile * T + t;
-    if (u < Reg3Cfg<N>::B1) {
-        cplx v[R1];
+    // grid == nwork: one tile per CTA; a smaller grid walks the tiles (the push exchange launches one CTA per SM so that
+    // the NVLink-bound stores of this kernel share the SMs with the HBM-bound S1 of the next x-plane chunk)
+    for (int64_t w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const int64_t o = w / ntile;
+        const int tile = (int)(w - o * ntile);
+        const int64_t bi = linemap_base(mi, o) + (int64_t)tile * T + t;
+        const int64_t bo = linemap_base(mo, o) + (int64_t)tile * T + t;
+        if (u < Reg3Cfg<N>::B1) {
+            cplx v[R1];
 #pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = in[bi + linemap_row(mi, u + r * M)];
-        Bfly<R1, INV>::run(v);
+            for (int r = 0; r < R1; ++r) v[r] = in[bi + linemap_row(mi, u + r * M)];
+            Bfly<R1, INV>::run(v);
 #pragma unroll
-        for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, INV));
+            for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, INV));
 #pragma unroll
-        for (int q = 0; q < R1; ++q) smc[(q * M + u) * T + t] = v[q];
-    }
-    __syncthreads();
-    if (u < Reg3Cfg<N>::B2) {
-        const int q = u / R3, jp = u - q * R3;
-        cplx* sp = smc + (q * M + jp) * T + t;
-        cplx v[R2];
+            for (int q = 0; q < R1; ++q) smc[(q * M + u) * T + t] = v[q];
+        }
+        __syncthreads();
+        if (u < Reg3Cfg<N>::B2) {
+            const int q = u / R3, jp = u - q * R3;
+            cplx* sp = smc + (q * M + jp) * T + t;
+            cplx v[R2];
 #pragma unroll
-        for (int r = 0; r < R2; ++r) v[r] = sp[r * R3 * T];
-        Bfly<R2, INV>::run(v);
+            for (int r = 0; r < R2; ++r) v[r] = sp[r * R3 * T];
+            Bfly<R2, INV>::run(v);
 #pragma unroll
-        for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, INV));
+            for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, INV));
 #pragma unroll
-        for (int q2 = 0; q2 < R2; ++q2) sp[q2 * R3 * T] = v[q2];
-    }
-    __syncthreads();
-    if (u < Reg3Cfg<N>::B3) {
-        const int q = u % R1, q2 = u / R1;
-        const cplx* sp = smc + (q * M + q2 * R3) * T + t;
-        cplx v[R3];
+            for (int q2 = 0; q2 < R2; ++q2) sp[q2 * R3 * T] = v[q2];
+        }
+        __syncthreads();
+        if (u < Reg3Cfg<N>::B3) {
+            const int q = u % R1, q2 = u / R1;
+            const cplx* sp = smc + (q * M + q2 * R3) * T + t;
+            cplx v[R3];
 #pragma unroll
-        for (int jp = 0; jp < R3; ++jp) v[jp] = sp[jp * T];
-        Bfly<R3, INV>::run(v);
+            for (int jp = 0; jp < R3; ++jp) v[jp] = sp[jp * T];
+            Bfly<R3, INV>::run(v);
 #pragma unroll
-        for (int k = 0; k < R3; ++k) out[bo + linemap_row(mo, u + R1 * R2 * k)] = v[k];
+            for (int k = 0; k < R3; ++k) out[bo + linemap_row(mo, u + R1 * R2 * k)] = v[k];
+        }
+        if (w + gridDim.x < nwork) __syncthreads();  // the tile buffer is refilled by the next round
     }
 }

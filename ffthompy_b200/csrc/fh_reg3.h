@@ -43,5 +43,10 @@ struct LineMap;
 bool fh_reg3_map_len(int n);
 int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
                           int pitch, const int64_t* rowoff, int64_t cstride);
+// max_ctas > 0: persistent launch with at most that many CTAs walking the tiles (0: one CTA per tile)
 int fh_reg3_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
-                    int64_t panels, int pitch, bool inv);
+                    int64_t panels, int pitch, bool inv, int max_ctas = 0);
+// push mode of the slab pipeline: S3 reads the natural y-slab spectrum `data` and writes row i0 of component c to
+// dout[c*cstride_out + rowoff_out[i0] + ii] (the x-slab spectrum of the rank that owns plane i0, peer-mapped)
+int fh_reg3_mid_green_push(int N, int kind, cplx* data, cplx* dout, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
+                           int pitch, const int64_t* rowoff_out, int64_t cstride_out);

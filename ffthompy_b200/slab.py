@@ -10,8 +10,13 @@ operator application is
     S4, S5  local
 and CG reduces its two scalars per iteration with all-reduce (device tensors, no host round trip).
 
-Three exchange modes:
-* peer (default on NVLink-connected GPUs when N0 is a power of two 16..2048): the x-slab spectra live in
+Exchange modes:
+* push (default on NVLink-connected GPUs for N0 in {128, 256, 512}; csrc/fh_slab2.cu): both spectrum layouts live in
+  torch symmetric memory; S2 STORES every output row k1 straight into the y-slab spectrum of the rank that owns k1 and
+  S3 stores every output row i0 into the x-slab spectrum of the owner of plane i0.  No exchange buffer, no copy
+  engine or NCCL traffic, no remote loads (stores are fire-and-forget, so the NVLink transfer overlaps the transforms
+  of the producing kernel), six kernels and two device barriers per operator application.
+* peer (N0 a power of two 16..2048): the x-slab spectra live in
   torch symmetric memory (peer-mapped over NVLink); S3 of each rank gathers its rows straight from the
   owners' spectra with remote loads, applies G^ and scatters the result back with remote stores
   (fh_ga_slab_peer).  The exchange is fused into the axis-0 kernel — no all-to-all, no exchange buffer,
@@ -107,7 +112,7 @@ def direct_offsets(layout, D, P, nchunk):
     return off1, off0, n0c*inner, inner, n0c*inner, G*D*n0c*inner
 
 
-def best_exchange(A_local, G, N, group=None, modes=('peer', 'p2p'), reps=3):
+def best_exchange(A_local, G, N, group=None, modes=('push', 'p2p'), reps=3):
     """Measure, don't guess: build the operator with each exchange mode in `modes`, time `reps` applications on
     the device (max over ranks, so every rank takes the same decision) and return (name, {name: ms}).  Modes
     whose kernels or memory mappings are not available here are skipped; which one wins depends on grid size
@@ -166,23 +171,30 @@ class SlabGA(object):
         self.D = D = int(A_local.shape[0])
         assert tuple(A_local.shape) == (D, D, lay.n0l, lay.N[1], lay.N[2])
         assert G.lazy and G.fft_form == 'r' and tuple(int(n) for n in G.N) == lay.N
-        assert exchange in (None, 'peer', 'p2p', 'direct', 'packed')
+        assert exchange in (None, 'push', 'peer', 'p2p', 'direct', 'packed')
         self.A = A_local.contiguous()
         self.plan = dev.plan(lay.N)
         lib = dev.lib()
         nwork = int(lib.fh_ga_slab_work_doubles(self.plan, D, lay.n0l, lay.n1l))
         # peer mode: the workspace (with the spectrum inside) is symmetric memory, mapped by every rank
         self.symm = None
-        if exchange in (None, 'peer') and world > 1:
+        if exchange in (None, 'push', 'peer') and world > 1:
+            # the allocation is local, the rendezvous collective: agree on the former before entering the latter
+            # (a rank that fell back on its own would leave its peers blocked inside the rendezvous)
+            work = None
             try:
                 import torch.distributed._symmetric_memory as symm_mem
-                self.work = symm_mem.empty(nwork, dtype=torch.float64, device=dev.device())
-                self.work.zero_()
-                self.symm = symm_mem.rendezvous(self.work, group if group is not None else dist.group.WORLD)
+                work = symm_mem.empty(nwork, dtype=torch.float64, device=dev.device())
+                work.zero_()
+                torch.cuda.synchronize()
             except Exception:
-                if exchange == 'peer':
-                    raise
-                self.symm = None
+                work = None
+            if self._agree(work is not None):
+                self.work = work
+                self.symm = symm_mem.rendezvous(self.work, group if group is not None else dist.group.WORLD)
+                dist.barrier(group=group)      # every rank's zero fill is complete before any peer may store into it
+            elif exchange in ('push', 'peer'):
+                raise RuntimeError('symmetric memory is not available on every rank (exchange=%r)' % exchange)
         if self.symm is None:
             self.work = dev.zeros((nwork,))
         self.handle = C.c_void_p()
@@ -204,7 +216,25 @@ class SlabGA(object):
         self.exchanged_bytes = 0
         self.sums = dev.zeros((2,))
         self.mode, self.nchunk = 'packed', 1
-        if exchange in (None, 'peer') and (self.symm is not None or world == 1):
+        if exchange in (None, 'push') and (self.symm is not None or world == 1):
+            if self.symm is not None:
+                pS = [int(b)+(spec.value-base) for b in self.symm.buffer_ptrs]
+                pT = [int(b)+(specT.value-base) for b in self.symm.buffer_ptrs]
+            else:
+                pS, pT = [spec.value], [specT.value]
+            rc = lib.fh_ga_slab_push(self.handle, world, rank, (C.c_void_p*world)(*pS), (C.c_void_p*world)(*pT))
+            if self._agree(rc == 0):
+                self.mode = 'push'
+                # x-plane chunks of S1 | S2: S2 (NVLink stores) of chunk j runs on a side stream under S1 (HBM) of j+1
+                import os
+                want = int(nchunk) if nchunk else int(os.environ.get('FH_PUSH_CHUNKS', '4'))
+                need = 8 if (lay.N[2] & (lay.N[2]-1)) == 0 else 24      # rows per S1 launch: a multiple of its rows per CTA
+                rows_ok = lambda J: lay.n0l % J == 0 and ((lay.n0l//J)*lay.N[1]) % need == 0   # noqa: E731
+                self.nchunk = max([J for J in (8, 4, 2, 1) if J <= max(want, 1) and (J == 1 or rows_ok(J))])
+                self.side = torch.cuda.Stream() if self.nchunk > 1 else None
+            elif exchange == 'push':
+                L.check(rc if rc else -3)
+        if self.mode == 'packed' and exchange in (None, 'peer') and (self.symm is not None or world == 1):
             if self.symm is not None:
                 ptrs = [int(b)+(spec.value-base) for b in self.symm.buffer_ptrs]
                 assert ptrs[rank] == spec.value
@@ -212,10 +242,10 @@ class SlabGA(object):
                 ptrs = [spec.value]
             arr = (C.c_void_p*world)(*ptrs)
             rc = lib.fh_ga_slab_peer(self.handle, world, rank, arr)
-            if rc == 0:
+            if self._agree(rc == 0):
                 self.mode = 'peer'
             elif exchange == 'peer':
-                L.check(rc)
+                L.check(rc if rc else -3)
         if self.mode == 'packed' and exchange in (None, 'direct', 'p2p'):
             cands = [int(nchunk)] if nchunk else [j for j in (4, 2, 1) if lay.n0l % j == 0]
             nel = D*lay.n0l*lay.N[1]*P
@@ -240,7 +270,7 @@ class SlabGA(object):
             rc = -1
             for J in cands:
                 rc = lib.fh_ga_slab_direct(self.handle, world, J, dev.ptr(bufA), dev.ptr(bufB))
-                if rc == 0:
+                if self._agree(rc == 0):
                     self.mode, self.nchunk = 'direct', J
                     self.bufA, self.bufB = bufA.view(J, -1), bufB.view(J, -1)
                     break
@@ -262,6 +292,19 @@ class SlabGA(object):
                 self.cstreams = [torch.cuda.Stream() for _ in range(nside)]
                 self.nsplit = max(1, nside//max(1, world-1))   # pieces per remote block when peers are few
         self.direct = self.mode in ('direct', 'p2p')
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=group)          # set-up complete on every rank before the first operator application
+
+    def _agree(self, ok):
+        """collective AND over the ranks: every rank takes the same exchange mode"""
+        import torch
+        import torch.distributed as dist
+        if dist.get_world_size(self.group) == 1:
+            return bool(ok)
+        t = torch.tensor([1 if ok else 0], dtype=torch.int32, device=self.dev.device())
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(t.item())
 
     def _barrier(self):
         """device-side barrier across the ranks on the current stream (symmetric-memory signal pads)"""
@@ -276,9 +319,48 @@ class SlabGA(object):
             pass
 
     def _stage(self, s, chunk, p, r, pupdate, y):
+        if self.mode == 'push':
+            self._pstage(s, 0, 1, p, r, pupdate, y)
+            return
         self.L.check(self.dev.lib().fh_ga_slab_stage(self.handle, s, chunk, self.dev.ptr(p),
                                                      self.dev.ptr(r) if r is not None else None, int(pupdate),
                                                      self.dev.ptr(y)))
+
+    def _pstage(self, s, chunk, nchunk, p, r, pupdate, y):
+        self.L.check(self.dev.lib().fh_ga_slab_push_stage(self.handle, s, int(chunk), int(nchunk), self.dev.ptr(p),
+                                                          self.dev.ptr(r) if r is not None else None,
+                                                          int(pupdate), self.dev.ptr(y)))
+
+    def _apply_push(self, x, y, r, pupdate):
+        """S1 | S2 chunked over x-planes on two streams, barrier, S3 (stores into the owners' x-slabs), barrier, S4, S5"""
+        import torch
+        J = self.nchunk
+        lib, L = self.dev.lib(), self.L
+        if J == 1:
+            self._pstage(1, 0, 1, x, r, pupdate, y)
+            self._pstage(2, 0, 1, x, r, 0, y)
+        else:
+            main, side = torch.cuda.current_stream(), self.side
+            side.wait_stream(main)            # the previous application's S4 has read this rank's x-slab spectrum
+            for j in range(J):
+                self._pstage(1, j, J, x, r, pupdate, y)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                L.check(lib.fh_set_stream(C.c_void_p(side.cuda_stream)))
+                try:
+                    self._pstage(2, j, J, x, r, 0, y)
+                finally:
+                    L.check(lib.fh_set_stream(C.c_void_p(main.cuda_stream)))
+            main.wait_stream(side)
+        self._barrier()                      # every rank's S2 rows are in place
+        self._pstage(3, 0, 1, x, r, 0, y)
+        self._barrier()                      # every rank's S3 rows are back
+        self._pstage(4, 0, 1, x, r, 0, y)
+        self._pstage(5, 0, 1, x, r, 0, y)
+        lay = self.layout
+        self.exchanged_bytes += 2*self.spec.numel()*16*(lay.world-1)//lay.world
+        return y
 
     def _a2a(self, dst, src):
         """one exchange block; returns a work handle (None on a single rank)"""
@@ -294,11 +376,13 @@ class SlabGA(object):
         update x <- r + beta*x (beta on the device) is folded into S1, as in fh_cg_steps."""
         if y is None:
             y = self.dev.empty(x.shape)
-        if self.mode == 'peer':
+        if self.mode == 'push':
+            return self._apply_push(x, y, r, pupdate)
+        if self.mode in ('peer', 'push'):
             self._stage(1, 0, x, r, pupdate, y)
-            self._stage(2, 0, x, r, 0, y)
+            self._stage(2, 0, x, r, 0, y)        # push: rows stored into the owners' y-slab spectra
             self._barrier()                      # every rank's S2 output is in place
-            self._stage(3, 0, x, r, 0, y)        # remote loads -> G^ -> remote stores
+            self._stage(3, 0, x, r, 0, y)        # peer: remote loads -> G^ -> remote stores; push: local loads, remote stores
             self._barrier()                      # every rank's rows are back
             self._stage(4, 0, x, r, 0, y)
             self._stage(5, 0, x, r, 0, y)

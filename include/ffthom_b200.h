@@ -150,6 +150,16 @@ int fh_ga_slab_direct(fh_ga* op, int world, int nchunk, void* bufA, void* bufB);
  * memory), applies G^ and stores the result back in place.  The caller issues a device barrier across
  * the ranks before and after stage 3 of fh_ga_slab_stage.  N0 in {16,...,2048} powers of two. */
 int fh_ga_slab_peer(fh_ga* op, int world, int rank, const void* const* peer_spec);
+/* "Push" exchange (csrc/fh_slab2.cu): S2 stores every output row k1 into the y-slab spectrum of the rank that owns
+ * k1, S3 stores every output row i0 into the x-slab spectrum of the rank that owns plane i0 (NVLink peer stores, no
+ * remote loads, no exchange buffer, no extra pass).  peer_spec[g] / peer_specT[g] = rank g's fh_ga_buffers pointers as
+ * mapped into this process (symmetric memory).  fh_ga_slab_push_stage runs stage 1..5 with the CG fusions; the caller
+ * places a device barrier across the ranks between stages 2|3 and 3|4.  Replaces one Afun(P) of general/solver.py:125
+ * on a decomposed field.  Stages 1 and 2 work on x-plane chunk `chunk` of `nchunk` (S2 of one chunk is NVLink-bound,
+ * S1 of the next HBM-bound: run on two streams they overlap).  N0 in {128, 256, 512}, N1 a power of two 16..2048. */
+int fh_ga_slab_push(fh_ga* op, int world, int rank, const void* const* peer_spec, const void* const* peer_specT);
+int fh_ga_slab_push_stage(fh_ga* op, int stage, int chunk, int nchunk, double* p, const double* r, int pupdate,
+                          double* y);
 /* one pipeline step with the CG fusions of fh_cg_steps (p = r + beta p in S1 when pupdate, <p,y> in S5):
  * plain stages 1..5 without fh_ga_slab_direct; with it stage 1 = S1+S2 of `chunk` -> bufA,
  * 3 = S3 on bufB, 4 = S4+S5 of `chunk` from bufA.  Replaces one Afun(P) of general/solver.py:125 */

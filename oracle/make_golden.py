@@ -388,7 +388,49 @@ def gen_round2(big=True):
     print('round2.npz: %d arrays' % len(out))
 
 
+# ----------------------------------------------------------------------------- 6. potential (displacement-based) formulation
+def gen_potential():
+    """ffthompy/tensorsLowRank/homogenisation.py:13-128 (homog_Ga_full, homog_Ga_full_potential,
+    homog_GaNi_full_potential) run UNMODIFIED on the SURVEY App. C material (square 0.6, 10:1, order 0, P = 5); the
+    module imports ttpy, which is absent here and unused on this path, so an empty stand-in is registered for it."""
+    import types
+    for m in ('tt', 'tt.core', 'tt.core.vector'):
+        sys.modules.setdefault(m, types.ModuleType(m))
+    sys.modules['tt.core.vector'].vector = type('vector', (), {})
+    from ffthompy import Struct
+    from ffthompy.tensorsLowRank.homogenisation import homog_Ga_full_potential, homog_Ga_full, homog_GaNi_full_potential
+    out = {}
+    for dim, n in ((2, 5), (3, 5), (2, 15), (2, 16), (3, 9)):
+        N = n*np.ones(dim, dtype=int)
+        Nbar = 2*N-1
+        mat = {'inclusions': ['square', 'otherwise'], 'positions': [np.zeros(dim), ''], 'params': [0.6*np.ones(dim), ''],
+               'vals': [10*np.eye(dim), 1.*np.eye(dim)], 'Y': np.ones(dim), 'order': 0, 'P': 5*np.ones(dim, dtype=int)}
+        Aga = quiet(Material(mat).get_A_Ga, Nbar, 'primal')
+        Agani = quiet(Material(mat).get_A_GaNi, N, 'primal')
+        pars = Struct(dim=dim, N=N, Y=np.ones(dim), solver=dict(tol=1e-8, maxiter=200))
+        rP = quiet(homog_Ga_full_potential, Aga, pars)
+        rF = quiet(homog_Ga_full, Aga, pars)
+        rG = quiet(homog_GaNi_full_potential, Agani, Aga, pars)
+        rG0 = quiet(homog_GaNi_full_potential, Agani, None, pars)
+        tag = 'pot_d%d_n%d' % (dim, n)
+        out[tag+'_Aga'], out[tag+'_Agani'] = Aga.val, Agani.val
+        out[tag+'_AH_Ga_potential'], out[tag+'_kit_Ga_potential'] = rP.AH, rP.info['kit']
+        out[tag+'_normres_Ga_potential'] = rP.info['norm_res']
+        out[tag+'_Fu_Ga_potential'] = rP.Fu.val
+        out[tag+'_e_Ga_potential'] = rP.e.val
+        out[tag+'_AH_Ga_gradient'] = rF.AH
+        out[tag+'_AH_GaNi_potential_Ga'], out[tag+'_kit_GaNi_potential'] = rG.AH, rG.info['kit']
+        out[tag+'_AH_GaNi_potential_GaNi'] = rG0.AH
+        print('  potential dim=%d N=%d: Ga %.15g (%d its; gradient-field %.15g), GaNi->Ga %.15g (%d its), GaNi %.15g'
+              % (dim, n, rP.AH, rP.info['kit'], rF.AH, rG.AH, rG.info['kit'], rG0.AH))
+    np.savez_compressed(os.path.join(OUT, 'potential.npz'), **out)
+    print('potential.npz: %d arrays' % len(out))
+
+
 if __name__ == '__main__':
+    if '--potential' in sys.argv:
+        gen_potential()
+        sys.exit(0)
     if '--round2' in sys.argv:          # leaves the round-1 files untouched
         gen_round2(big='--small' not in sys.argv)
         sys.exit(0)
@@ -397,4 +439,5 @@ if __name__ == '__main__':
     gen_configs()
     gen_examples()
     gen_round2()
+    gen_potential()
     os.system('ls -la %s' % OUT)

@@ -31,7 +31,7 @@ def main():
     from ffthompy_b200.slab import SlabGA, SlabLayout
     dev.init(local)
     ok = True
-    for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20), (32, 16, 15), (128, 256, 32), (512, 16, 16),
+    for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20), (32, 16, 15), (128, 256, 32), (128, 16, 24), (256, 32, 16), (512, 16, 16),
                                                      (16, 512, 16), (16, 16, 512)]):
         if N[0] % world or N[1] % world or (world > 2 and np.prod(N) > 300000):
             continue
@@ -49,12 +49,12 @@ def main():
         E[0] = 1.
         B = Afo(-E)
         xo, io = O.cg(Afo, B, np.zeros_like(B), 1e-6, 1000, N)
-        for mode in ('packed', 'direct', 'direct1', 'peer') + (('p2p',) if world > 1 else ()):
+        for mode in ('packed', 'direct', 'direct1', 'peer', 'push') + (('p2p',) if world > 1 else ()):
             try:
                 op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N, exchange=mode.rstrip('1'),
                             nchunk=(1 if mode == 'direct1' else None))
             except Exception as e:
-                if 'not in the' not in str(e) and 'cannot run' not in str(e):
+                if 'not in the' not in str(e) and 'cannot run' not in str(e) and 'push variant' not in str(e):
                     raise
                 if rank == 0:
                     print('N=%s world=%d %s: exchange kernels do not cover this grid' % (N, world, mode))
@@ -129,7 +129,7 @@ def main():
                   '%.3e voxel-DOF/s, %.1f%% of the aggregate HBM roofline; NVLink %.2f GB sent per GPU per iteration'
                   % (op.mode, op.nchunk, kind, n, world, per*1e3, 1./per, D*nvox/per,
                      100*rec['hbm_roofline_frac'], nv/1e9), flush=True)
-        if '--profile' in sys.argv and op.mode in ('peer', 'p2p', 'direct'):
+        if '--profile' in sys.argv and op.mode in ('peer', 'push', 'p2p', 'direct'):
             xp = dev.zeros((D, lay.n0l)+N[1:])
             xp.normal_()
             marks = op.profile_apply(xp)
@@ -137,7 +137,7 @@ def main():
                 print('profile [ms] (%s, J=%d): ' % (op.mode, op.nchunk)+' | '.join('%s %.3f' % kv for kv in marks.items()),
                       flush=True)
             del xp
-        if '--stages' in sys.argv and op.mode in ('peer', 'packed'):
+        if '--stages' in sys.argv and op.mode in ('peer', 'push', 'packed'):
             # per-stage device time with every rank inside the same stage (barrier in front of each launch)
             x = dev.zeros((D, lay.n0l)+N[1:])
             x.normal_()

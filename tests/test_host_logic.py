@@ -16,7 +16,7 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
 def _header_symbols():
     src = open(os.path.join(ROOT, 'include', 'ffthom_b200.h')).read()
     src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
-    return sorted(set(re.findall(r'\b(fh_[a-z0-9_]+)\s*\(', src)))
+    return sorted(set(re.findall(r'\b(fh_[A-Za-z0-9_]+)\s*\(', src)))
 
 
 def test_library_exports_every_declared_symbol():
