@@ -5,6 +5,9 @@ loop behind FFTHomPy's own operator API.
     import ffthompy_b200.projections as proj
     from ffthompy_b200.general.solver import linear_solver
     from ffthompy_b200 import trigpol, matvecs
+    from ffthompy_b200.materials import Material              # get_A_GaNi / get_A_Ga on the device
+    from ffthompy_b200.postprocess import postprocess         # one-pass A_H assembly, bounds driver
+    from ffthompy_b200 import homogenisation                  # potential (displacement-based) formulation
 
 mirror ffthompy.tensors / ffthompy.projections / ffthompy.general.solver / ffthompy.trigpol /
 ffthompy.matvecs (same names, arguments and error behaviour); `install()` splices them into an
@@ -26,14 +29,14 @@ def install(reference_package='ffthompy'):
     Call before importing the reference's callers."""
     import importlib
     ref = importlib.import_module(reference_package)  # the reference tree must be importable
-    from . import tensors, projections, trigpol, postprocess
+    from . import tensors, projections, trigpol, postprocess, materials
     from .tensors import objects, operators, projection, fft
     from .general import solver, solver_pp
     mapping = {
         'tensors': tensors, 'tensors.objects': objects, 'tensors.operators': operators,
         'tensors.projection': projection, 'tensors.fft': fft, 'projections': projections,
         'general.solver': solver, 'general.solver_pp': solver_pp, 'trigpol': trigpol,
-        'postprocess': postprocess,
+        'postprocess': postprocess, 'materials': materials,
     }
     for name, mod in mapping.items():
         sys.modules[reference_package+'.'+name] = mod

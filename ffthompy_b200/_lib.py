@@ -62,6 +62,10 @@ _SIGNATURES = {
     'fh_contract_first': (c_int, [c_i64, c_int, c_int, c_vp, c_vp, c_vp]),
     'fh_inv_dxd': (c_int, [c_int, c_i64, c_vp, c_vp]),
     'fh_assemble_AH': (c_int, [c_int, c_int, c_i64, c_vp, C.POINTER(c_vp), p_dbl]),
+    'fh_topologies': (c_int, [c_int, p_i64, c_vp, p_dbl, c_int, p_int, p_dbl, p_dbl, c_vp, p_int]),
+    'fh_combine_phases': (c_int, [c_int, c_int, c_i64, p_dbl, c_vp, c_vp]),
+    'fh_sep_product': (c_int, [c_int, p_i64, c_vp, c_int, c_vp, c_vp]),
+    'fh_gather_periodic': (c_int, [c_int, p_i64, p_i64, p_i64, c_int, c_vp, c_vp]),
     'fh_spec_remap': (c_int, [c_int, p_i64, c_int, p_i64, c_int, c_i64, c_dbl, c_int, c_vp, c_vp]),
     'fh_roll': (c_int, [c_int, p_i64, p_i64, c_int, c_i64, c_vp, c_vp]),
     'fh_grad': (c_int, [c_int, p_i64, p_dbl, c_int, c_int, c_vp, c_vp]),
@@ -81,6 +85,9 @@ _SIGNATURES = {
     'fh_ga_slab_peer': (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp)]),
     'fh_ga_slab_push': (c_int, [c_vp, c_int, c_int, C.POINTER(c_vp), C.POINTER(c_vp)]),
     'fh_ga_slab_push_stage': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
+    'fh_ga_slab_kblock': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    'fh_ga_slab_kblock_info': (c_int, [c_vp, c_int, p_i64, p_i64, p_int, p_int]),
+    'fh_ga_slab_kblock_stage': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'fh_ga_slab_stage': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp]),
     'fh_cgd_init': (c_int, [c_vp, c_vp, c_vp]),
     'fh_cgd_update': (c_int, [c_vp, c_vp, c_vp]),

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ['fh_fft.cu', 'fh_pointwise.cu', 'fh_fused.cu', 'fh_reg3.cu', 'fh_mid2.cu', 'fh_slab2.cu']
+SOURCES = ['fh_fft.cu', 'fh_pointwise.cu', 'fh_fused.cu', 'fh_reg3.cu', 'fh_mid2.cu', 'fh_slab2.cu', 'fh_material.cu']
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith('.cuh') or f.endswith('.h')) + [os.path.join('..', '..', 'include', 'ffthom_b200.h')]
 LIB = os.path.join(PKG, 'libffthom_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')

@@ -998,6 +998,7 @@ extern "C" int fh_ga_destroy(fh_ga* op) {
     if (op->lut) cudaFree(op->lut);
     if (op->sd_off1) cudaFree(op->sd_off1);
     if (op->sp_off1) cudaFree(op->sp_off1);
+    if (op->kb_off) cudaFree(op->kb_off);
     cudaFree(op->scal);
     cudaFreeHost(op->pinned);
     free(op);

@@ -60,6 +60,13 @@ struct fh_ga {
     int sp_world;       // 0: off
     int64_t* sp_off1;   // device [N1]: S2 output row k1 -> element offset from this rank's specT (peer-mapped memory)
     int64_t* sp_off0;   // device [N0]: S3 output row i0 -> element offset from this rank's spec
+    // k2-block exchange pipeline (fh_slab2.cu): exchange buffers [block][G][D][n0l][n1l][w_block]
+    int kb_world, kb_nblk;
+    int kb_col0[16], kb_w[16];   // first spectrum column and width (multiples of 8) of every block
+    int64_t kb_base[16];         // element offset of block b inside bufA / bufB
+    int64_t* kb_off;             // device: per block [N1] axis-1 row offsets, then per block [N0] axis-0 row offsets
+    cplx* kb_bufA;               // S2 output / S4 input of this rank (x-slab side)
+    cplx* kb_bufB;               // S3 in place (y-slab side)
 };
 
 // internals of fh_fused.cu used by fh_slab2.cu

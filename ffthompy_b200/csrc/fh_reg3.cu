@@ -74,14 +74,14 @@ int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
 template <int N, int T, int KIND, int DIM>
 static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
                   const int64_t* rowoff = nullptr, int64_t cstride = 0, cplx* dout = nullptr,
-                  const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0) {
+                  const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0, int kcol0 = 0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int NT = 768;
     const size_t smem = (size_t)D * (N + N / 8) * T * sizeof(cplx);
     int rc;
     if ((rc = reg3_smem_attr(k_mid_green_reg3<N, T, KIND, DIM, NT>, smem))) return rc;
     k_mid_green_reg3<N, T, KIND, DIM, NT><<<(unsigned)(inner / T), NT, smem, fh_stream()>>>(
-        data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner, dout, rowoff_out, cstride_out);
+        data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner, dout, rowoff_out, cstride_out, kcol0);
     FH_LAUNCH_CHECK();
     return FH_OK;
 }
@@ -113,11 +113,13 @@ bool fh_reg3_map_len(int n) {
     return n == 512 || (n == 256 && m256);
 }
 int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
-                          int pitch, const int64_t* rowoff, int64_t cstride) {
+                          int pitch, const int64_t* rowoff, int64_t cstride, int kcol0) {
     if (N == 512 && inner % 4 == 0) {
-        if (kind == FH_GREEN_SCALAR) return mid_KD<512, 4, FH_GREEN_SCALAR, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
-        return mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
+        if (kind == FH_GREEN_SCALAR)
+            return mid_KD<512, 4, FH_GREEN_SCALAR, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride, nullptr, nullptr, 0, kcol0);
+        return mid_KD<512, 4, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride, nullptr, nullptr, 0, kcol0);
     }
+    if (kcol0) return fh_set_error(FH_ERR_UNSUPPORTED, "three-pass axis-0 exchange kernel: column blocks need N0 = 512");
     if (N == 256 && inner % 8 == 0 && kind == FH_GREEN_ELASTIC)
         return mid_KD<256, 8, FH_GREEN_ELASTIC, 3>(data, tw, g, inner, nh, pitch, rowoff, cstride);
     return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass axis-0 exchange kernel for N0=%d", N);

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(NT, 1)
     k_mid_green_reg3(cplx* __restrict__ data, const cplx* __restrict__ tw, GreenDesc g, int64_t inner, int nh,
                      int pitch, const int64_t* __restrict__ rowoff, int64_t cstride,
                      cplx* __restrict__ dout = nullptr, const int64_t* __restrict__ rowoff_out = nullptr,
-                     int64_t cstride_out = 0) {
+                     int64_t cstride_out = 0, int kcol0 = 0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
     constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
     constexpr int B1 = Reg3Cfg<N>::B1, B2 = Reg3Cfg<N>::B2, B3 = Reg3Cfg<N>::B3;
@@ -337,7 +337,8 @@ __global__ void __launch_bounds__(NT, 1)
         const int64_t ii = i0 + tt;
         bool valid = true;
         if (DIM == 3) {
-            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch);
+            // (kcol0: first global column of a k2-block exchange buffer whose rows hold `pitch` columns)
+            const int i1 = (int)(ii / pitch), i2 = (int)(ii - (int64_t)i1 * pitch) + kcol0;
             k[1] = fh_freq(i1 + g.ioff1, g.N[1]);
             k[2] = fh_freq(i2, g.N[2]);
             valid = i2 < nh;

@@ -41,8 +41,9 @@ int fh_reg3_mid_green(int N, int kind, int dim, cplx* data, const cplx* tw, cons
 // slab-exchange layouts (LineMap of fh_fast.cuh; rowoff / cstride of fh_ga_slab_direct)
 struct LineMap;
 bool fh_reg3_map_len(int n);
+// kcol0: global column of buffer column 0 (k2-block exchange buffers whose rows hold `pitch` = block-width columns)
 int fh_reg3_mid_green_map(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,
-                          int pitch, const int64_t* rowoff, int64_t cstride);
+                          int pitch, const int64_t* rowoff, int64_t cstride, int kcol0 = 0);
 // max_ctas > 0: persistent launch with at most that many CTAs walking the tiles (0: one CTA per tile)
 int fh_reg3_c2c_map(int N, const cplx* tw, const cplx* in, cplx* out, const LineMap& mi, const LineMap& mo,
                     int64_t panels, int pitch, bool inv, int max_ctas = 0);

@@ -112,3 +112,98 @@ extern "C" int fh_ga_slab_push_stage(fh_ga* op, int stage, int chunk, int nchunk
     }
     return fh_set_error(FH_ERR_ARG, "fh_ga_slab_push_stage: stage %d", stage);
 }
+
+// ------------------------------------------------------------------ k2-block exchange pipeline
+// The half-spectrum columns are split into nblk blocks of whole 8-column tiles.  S2, the exchange, S3, the exchange back
+// and S4 are independent across blocks (only S1 and S5 need whole rows), so with the blocks in flight on the copy
+// engines the NVLink transfer of block b overlaps S2 / S3 / S4 of its neighbours and only one block's transfer per
+// direction is exposed (task 3):
+//   S1 (all rows)  |  for b: S2_b -> bufA_b, push bufA_b[g] -> peer g's bufB_b[me]
+//                  |  for b: (pushes of block b landed everywhere)  S3_b in place on bufB_b, push back into bufA_b
+//                  |  for b: (block b is back)  S4_b: bufA_b -> spectrum columns of block b   |  S5 (all rows)
+// Exchange buffers: block b = [G][D][n0l][n1l][w_b] complex at element offset kb_base[b]; on the x-slab side G indexes the
+// peer that owns the k1 range, on the y-slab side the peer that owns the x-planes, so every (block, peer) piece is one
+// contiguous copy.  bufA / bufB: D*n0l*N1*pitch complex each, zero-filled by the caller (symmetric memory).
+extern "C" int fh_ga_slab_kblock(fh_ga* op, int world, int nblk, void* bufA, void* bufB) {
+    FH_REQUIRE(op && bufA && bufB && bufA != bufB && world >= 1, "fh_ga_slab_kblock: bad argument");
+    const fh_plan* p = op->plan;
+    FH_REQUIRE(p->dim == 3, "fh_ga_slab_kblock: a 3-D slab operator is required");
+    FH_REQUIRE((int64_t)op->n0l * world == p->N[0] && (int64_t)op->n1l * world == p->N[1],
+               "fh_ga_slab_kblock: slab extents do not match world=%d", world);
+    const int N0 = p->N[0], N1 = p->N[1], P = op->pitch, n0l = op->n0l, n1l = op->n1l, D = op->D;
+    const int ntile = P / 8;
+    FH_REQUIRE(P % 8 == 0 && nblk >= 1 && nblk <= 16 && nblk <= ntile, "fh_ga_slab_kblock: %d blocks over %d tiles", nblk, ntile);
+    if (!(N0 == 512 || fh_mid2_can(N0)))
+        return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_kblock: N0=%d has no column-block variant of the axis-0 kernel", N0);
+    if (!fh_map_len_host(N1))
+        return fh_set_error(FH_ERR_UNSUPPORTED, "fh_ga_slab_kblock: N1=%d not in the mapped axis-1 kernel family", N1);
+    int64_t* h = (int64_t*)malloc(sizeof(int64_t) * (size_t)nblk * (N0 + N1));
+    if (!h) return fh_set_error(FH_ERR_ALLOC, "fh_ga_slab_kblock: out of host memory");
+    int c0 = 0;
+    for (int b = 0; b < nblk; ++b) {
+        const int tiles = ntile / nblk + (b < ntile % nblk ? 1 : 0);
+        const int w = tiles * 8;
+        op->kb_col0[b] = c0;
+        op->kb_w[b] = w;
+        op->kb_base[b] = (int64_t)D * n0l * N1 * c0;
+        const int64_t inner = (int64_t)n1l * w;
+        for (int k1 = 0; k1 < N1; ++k1) h[(size_t)b * N1 + k1] = (int64_t)(k1 / n1l) * D * n0l * inner + (int64_t)(k1 % n1l) * w;
+        for (int i0 = 0; i0 < N0; ++i0)
+            h[(size_t)nblk * N1 + (size_t)b * N0 + i0] = ((int64_t)(i0 / n0l) * D * n0l + (i0 % n0l)) * inner;
+        c0 += w;
+    }
+    if (op->kb_off) cudaFree(op->kb_off);
+    op->kb_off = NULL;
+    cudaError_t e = cudaMalloc((void**)&op->kb_off, sizeof(int64_t) * (size_t)nblk * (N0 + N1));
+    if (e == cudaSuccess) e = cudaMemcpy(op->kb_off, h, sizeof(int64_t) * (size_t)nblk * (N0 + N1), cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fh_set_error(FH_ERR_CUDA, "fh_ga_slab_kblock: %s", cudaGetErrorString(e));
+    op->kb_world = world;
+    op->kb_nblk = nblk;
+    op->kb_bufA = (cplx*)bufA;
+    op->kb_bufB = (cplx*)bufB;
+    return FH_OK;
+}
+
+// element offset of block `blk` inside the exchange buffers and the elements one peer receives from this rank
+extern "C" int fh_ga_slab_kblock_info(const fh_ga* op, int blk, int64_t* base, int64_t* per_peer, int* col0, int* width) {
+    FH_REQUIRE(op && op->kb_world >= 1 && blk >= 0 && blk < op->kb_nblk, "fh_ga_slab_kblock_info: bad block");
+    if (base) *base = op->kb_base[blk];
+    if (per_peer) *per_peer = (int64_t)op->D * op->n0l * op->n1l * op->kb_w[blk];
+    if (col0) *col0 = op->kb_col0[blk];
+    if (width) *width = op->kb_w[blk];
+    return FH_OK;
+}
+
+// stage 1: S1 (whole slab);  2: S2 of column block blk -> bufA;  3: S3 in place on block blk of bufB;
+// 4: S4 of block blk from bufA into the x-slab spectrum;  5: S5 (whole slab, partial sums of <p, y>)
+extern "C" int fh_ga_slab_kblock_stage(fh_ga* op, int stage, int blk, double* p, const double* r, int pupdate, double* y) {
+    FH_REQUIRE(op && p && y && op->kb_world >= 1, "fh_ga_slab_kblock_stage: fh_ga_slab_kblock has not been set up");
+    FH_REQUIRE(blk >= 0 && blk < op->kb_nblk, "fh_ga_slab_kblock_stage: block %d out of range", blk);
+    const fh_plan* pl = op->plan;
+    const int D = op->D, P = op->pitch, N0 = pl->N[0], N1 = pl->N[1], n0l = op->n0l, n1l = op->n1l;
+    const int w = op->kb_w[blk], c0 = op->kb_col0[blk];
+    const int64_t inner = (int64_t)n1l * w;
+    const int64_t* off1 = op->kb_off + (size_t)blk * N1;
+    const int64_t* off0 = op->kb_off + (size_t)op->kb_nblk * N1 + (size_t)blk * N0;
+    const LineMap nat = {NULL, (int64_t)P, (int64_t)n0l * N1 * P, (int64_t)N1 * P, n0l};
+    const LineMap blkmap = {off1, 0, (int64_t)n0l * inner, inner, n0l};
+    int np = 0;
+    switch (stage) {
+        case 1: return fh_ga_stage_local(op, 1, p, r, pupdate, y, 0, NULL);
+        case 2:
+            return fh_launch_c2c_map(N1, pl->ax[1].tw, op->spec + c0, op->kb_bufA + op->kb_base[blk], nat, blkmap,
+                                     (int64_t)D * n0l, w, false);
+        case 3:
+            if (N0 == 512)
+                return fh_reg3_mid_green_map(N0, op->g.kind, op->kb_bufB + op->kb_base[blk], pl->ax[0].tw, op->g, inner,
+                                             pl->nh, w, off0, (int64_t)n0l * inner, c0);
+            return fh_mid2_green(N0, op->g.kind, op->kb_bufB + op->kb_base[blk], pl->ax[0].tw, op->g, off0, 0,
+                                 (int64_t)n0l * inner, w, c0, pl->nh, n1l, 0, w);
+        case 4:
+            return fh_launch_c2c_map(N1, pl->ax[1].tw, op->kb_bufA + op->kb_base[blk], op->spec + c0, blkmap, nat,
+                                     (int64_t)D * n0l, w, true);
+        case 5: return fh_ga_stage_local(op, 5, p, NULL, 0, y, 1, &np);
+    }
+    return fh_set_error(FH_ERR_ARG, "fh_ga_slab_kblock_stage: stage %d", stage);
+}

@@ -16,6 +16,10 @@ Exchange modes:
   S3 stores every output row i0 into the x-slab spectrum of the owner of plane i0.  No exchange buffer, no copy
   engine or NCCL traffic, no remote loads (stores are fire-and-forget, so the NVLink transfer overlaps the transforms
   of the producing kernel), six kernels and two device barriers per operator application.
+* kblock (N0 in {128, 256, 512}; csrc/fh_slab2.cu): the half-spectrum columns are split into blocks of whole
+  8-column tiles.  S2, exchange, S3, exchange back and S4 are independent across blocks, so block b travels on the
+  copy engines (pushes into the peers' symmetric exchange buffers) while blocks b+-1 are transformed on the SMs; only
+  S1 and S5 need whole rows.  One block's transfer per direction is exposed instead of the whole exchange.
 * peer (N0 a power of two 16..2048): the x-slab spectra live in
   torch symmetric memory (peer-mapped over NVLink); S3 of each rank gathers its rows straight from the
   owners' spectra with remote loads, applies G^ and scatters the result back with remote stores
@@ -171,7 +175,7 @@ class SlabGA(object):
         self.D = D = int(A_local.shape[0])
         assert tuple(A_local.shape) == (D, D, lay.n0l, lay.N[1], lay.N[2])
         assert G.lazy and G.fft_form == 'r' and tuple(int(n) for n in G.N) == lay.N
-        assert exchange in (None, 'push', 'peer', 'p2p', 'direct', 'packed')
+        assert exchange in (None, 'kblock', 'push', 'peer', 'p2p', 'direct', 'packed')
         self.A = A_local.contiguous()
         self.plan = dev.plan(lay.N)
         lib = dev.lib()
@@ -231,9 +235,12 @@ class SlabGA(object):
                 need = 8 if (lay.N[2] & (lay.N[2]-1)) == 0 else 24      # rows per S1 launch: a multiple of its rows per CTA
                 rows_ok = lambda J: lay.n0l % J == 0 and ((lay.n0l//J)*lay.N[1]) % need == 0   # noqa: E731
                 self.nchunk = max([J for J in (8, 4, 2, 1) if J <= max(want, 1) and (J == 1 or rows_ok(J))])
-                self.side = torch.cuda.Stream() if self.nchunk > 1 else None
+                # high priority: the few persistent S2 CTAs must win the SM slots that S1 frees, or they queue behind all of S1
+                self.side = torch.cuda.Stream(priority=-1) if self.nchunk > 1 else None
             elif exchange == 'push':
                 L.check(rc if rc else -3)
+        if self.mode == 'packed' and exchange == 'kblock':
+            self._setup_kblock(nchunk)
         if self.mode == 'packed' and exchange in (None, 'peer') and (self.symm is not None or world == 1):
             if self.symm is not None:
                 ptrs = [int(b)+(spec.value-base) for b in self.symm.buffer_ptrs]
@@ -295,6 +302,105 @@ class SlabGA(object):
         if world > 1:
             torch.cuda.synchronize()
             dist.barrier(group=group)          # set-up complete on every rank before the first operator application
+
+    def _setup_kblock(self, nblk):
+        """exchange buffers in symmetric memory + block tables (fh_ga_slab_kblock)"""
+        import os
+        import torch
+        import torch.distributed as dist
+        L, dev, lay, D, P = self.L, self.dev, self.layout, self.D, self.pitch
+        lib = dev.lib()
+        world, rank = lay.world, lay.rank
+        nel = D*lay.n0l*lay.N[1]*P
+        cview = lambda t: torch.view_as_complex(t.reshape(-1, 2))    # noqa: E731
+        self.xsymm = None
+        if world > 1:
+            import torch.distributed._symmetric_memory as symm_mem
+            xb = symm_mem.empty(4*nel, dtype=torch.float64, device=dev.device())
+            xb.zero_()
+            torch.cuda.synchronize()
+            self.xsymm = symm_mem.rendezvous(xb, self.group if self.group is not None else dist.group.WORLD)
+            dist.barrier(group=self.group)
+        else:
+            xb = dev.zeros((4*nel,))
+        self._xb = xb
+        bufA, bufB = cview(xb[:2*nel]), cview(xb[2*nel:])
+        J = int(nblk) if nblk else int(os.environ.get('FH_KBLOCKS', '3'))
+        J = max(1, min(J, P//8, 16))
+        rc = lib.fh_ga_slab_kblock(self.handle, world, J, dev.ptr(bufA), dev.ptr(bufB))
+        if not self._agree(rc == 0):
+            L.check(rc if rc else -3)
+        self.mode, self.nchunk = 'kblock', J
+        self.kbufA, self.kbufB = bufA, bufB
+        self.kinfo = []
+        for b in range(J):
+            base, per = C.c_int64(), C.c_int64()
+            L.check(lib.fh_ga_slab_kblock_info(self.handle, b, C.byref(base), C.byref(per), None, None))
+            self.kinfo.append((int(base.value), int(per.value)))
+        self.kpeerA, self.kpeerB = [], []
+        for g_ in range(world):
+            if self.xsymm is not None:
+                pb = self.xsymm.get_buffer(g_, (4*nel,), torch.float64, 0)
+                self.kpeerA.append(cview(pb[:2*nel]))
+                self.kpeerB.append(cview(pb[2*nel:]))
+            else:
+                self.kpeerA.append(bufA)
+                self.kpeerB.append(bufB)
+        self.kstreams = (torch.cuda.Stream(), torch.cuda.Stream())   # forward / backward copy streams
+
+    def _kstage(self, s, blk, p, r, pupdate, y):
+        self.L.check(self.dev.lib().fh_ga_slab_kblock_stage(self.handle, s, int(blk), self.dev.ptr(p),
+                                                            self.dev.ptr(r) if r is not None else None,
+                                                            int(pupdate), self.dev.ptr(y)))
+
+    def _kpush(self, peers, src, blk):
+        """block `blk` of this rank's buffer `src`: piece g -> slot `rank` of block `blk` in peer g's buffer"""
+        G, me = self.layout.world, self.layout.rank
+        base, per = self.kinfo[blk]
+        for g in [(me+k) % G for k in range(1, G)]+[me]:
+            peers[g][base+me*per:base+(me+1)*per].copy_(src[base+g*per:base+(g+1)*per], non_blocking=True)
+
+    def _apply_kblock(self, x, y, r, pupdate):
+        import torch
+        J = self.nchunk
+        main = torch.cuda.current_stream()
+        csF, csB = self.kstreams
+        multi = self.xsymm is not None
+        self._kstage(1, 0, x, r, pupdate, y)
+        landed = []
+        for b in range(J):
+            self._kstage(2, b, x, r, 0, y)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            csF.wait_event(ev)
+            with torch.cuda.stream(csF):
+                self._kpush(self.kpeerB, self.kbufA, b)
+                if multi:
+                    self.xsymm.barrier(channel=0)          # block b of every rank has landed everywhere
+                e = torch.cuda.Event()
+                e.record(csF)
+                landed.append(e)
+        back = []
+        for b in range(J):
+            main.wait_event(landed[b])
+            self._kstage(3, b, x, r, 0, y)
+            ev = torch.cuda.Event()
+            ev.record(main)
+            csB.wait_event(ev)
+            with torch.cuda.stream(csB):
+                self._kpush(self.kpeerA, self.kbufB, b)
+                if multi:
+                    self.xsymm.barrier(channel=1)
+                e = torch.cuda.Event()
+                e.record(csB)
+                back.append(e)
+        for b in range(J):
+            main.wait_event(back[b])
+            self._kstage(4, b, x, None, 0, y)
+        self._kstage(5, 0, x, None, 0, y)
+        lay = self.layout
+        self.exchanged_bytes += 2*self.kbufA.numel()*16*(lay.world-1)//lay.world
+        return y
 
     def _agree(self, ok):
         """collective AND over the ranks: every rank takes the same exchange mode"""
@@ -378,6 +484,8 @@ class SlabGA(object):
             y = self.dev.empty(x.shape)
         if self.mode == 'push':
             return self._apply_push(x, y, r, pupdate)
+        if self.mode == 'kblock':
+            return self._apply_kblock(x, y, r, pupdate)
         if self.mode in ('peer', 'push'):
             self._stage(1, 0, x, r, pupdate, y)
             self._stage(2, 0, x, r, 0, y)        # push: rows stored into the owners' y-slab spectra
@@ -511,7 +619,14 @@ class SlabGA(object):
             marks[name] = float(t.item())
 
         timed('apply', lambda: self.apply(x, y))
-        if self.mode in ('p2p', 'direct'):
+        if self.mode == 'kblock':
+            timed('S1', lambda: self._kstage(1, 0, x, None, 0, y))
+            timed('S2', lambda: [self._kstage(2, b, x, None, 0, y) for b in range(J)])
+            timed('S3', lambda: [self._kstage(3, b, x, None, 0, y) for b in range(J)])
+            timed('S4', lambda: [self._kstage(4, b, x, None, 0, y) for b in range(J)])
+            timed('S5', lambda: self._kstage(5, 0, x, None, 0, y))
+            marks['exchange_exposed'] = marks['apply']-sum(marks['S%d' % k] for k in (1, 2, 3, 4, 5))
+        elif self.mode in ('p2p', 'direct'):
             timed('fwd_compute', lambda: [self._stage(1, j, x, None, 0, y) for j in range(J)])
             timed('S3', lambda: self._stage(3, 0, x, None, 0, y))
             timed('bwd_compute', lambda: [self._stage(4, j, x, None, 0, y) for j in range(J)])

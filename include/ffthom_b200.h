@@ -103,6 +103,20 @@ int fh_inv_dxd(int D, int64_t n, const double* A, double* Ainv);
  * AH_host[i*nsol+j] = sum over voxels of (A e_i).e_j, NOT divided by prod(N) */
 int fh_assemble_AH(int D, int nsol, int64_t n, const double* A, const double* const* sols_host, double* AH_host);
 
+/* ---- material coefficients (ffthompy/materials.py:54-425; set-up of the solve loop's largest input) -------------
+ * fh_topologies: characteristic functions of `ninc` inclusions (kind 0 cube, 1 ball, 2 pyramid, 3 otherwise, 4 all;
+ *   pos / par: ninc x 3 host arrays) at the nodes x_a[i_a] (`coords` = the per-axis coordinate vectors concatenated, device),
+ *   out [ninc][prod N]; *overlap_host != 0 if an 'otherwise' phase became negative (materials.py:296-297).
+ * fh_combine_phases: out[c] = sum_p coef[c][p] * chars[p]  (materials.py:203-204, :70-75).
+ * fh_sep_product: out[b][k] = (in ? in[b][k] : 1) * prod_a f_a[k_a], complex (weights of materials.py:318-390).
+ * fh_gather_periodic: out[b][j] = in[b][(start + j) mod P] per axis, complex (tile + decrease, materials.py:95-102). */
+int fh_topologies(int dim, const int64_t* N, const double* coords, const double* Y_host, int ninc, const int* kinds_host,
+                  const double* pos_host, const double* par_host, double* out, int* overlap_host);
+int fh_combine_phases(int ncomp, int nphase, int64_t n, const double* coef_host, const double* chars, double* out);
+int fh_sep_product(int dim, const int64_t* N, const double* factors, int batch, const double* in, double* out);
+int fh_gather_periodic(int dim, const int64_t* P, const int64_t* M, const int64_t* start, int batch, const double* in,
+                       double* out);
+
 /* ---- spectra: form changes, enlarge/decrease, shifts (tensors/objects.py:135-186,428-486;
  *      trigpol.py:162-214) ----------------------------------------------------------- */
 /* flags bit 0: trigpol.enlarge semantics (centred zero padding, no Nyquist splitting);
@@ -160,6 +174,16 @@ int fh_ga_slab_peer(fh_ga* op, int world, int rank, const void* const* peer_spec
 int fh_ga_slab_push(fh_ga* op, int world, int rank, const void* const* peer_spec, const void* const* peer_specT);
 int fh_ga_slab_push_stage(fh_ga* op, int stage, int chunk, int nchunk, double* p, const double* r, int pupdate,
                           double* y);
+/* k2-block exchange pipeline (csrc/fh_slab2.cu): the half-spectrum columns are split into nblk blocks of whole 8-column
+ * tiles; S2, exchange, S3, exchange back and S4 are independent across blocks, so block b travels on the copy engines
+ * while its neighbours are transformed.  bufA / bufB: zero-filled exchange buffers of D*n0_local*N1*pitch complex128,
+ * block b = [world][D][n0_local][n1_local][width_b] at element offset `base` (fh_ga_slab_kblock_info): the piece for
+ * peer g is the g-th of `world` contiguous runs of `per_peer` elements.  Stages: 1 = S1 (whole slab), 2 = S2 of block
+ * blk -> bufA, 3 = S3 in place on block blk of bufB, 4 = S4 of block blk from bufA, 5 = S5 (whole slab).
+ * N0 in {128, 256, 512}, N1 a power of two 16..2048. */
+int fh_ga_slab_kblock(fh_ga* op, int world, int nblk, void* bufA, void* bufB);
+int fh_ga_slab_kblock_info(const fh_ga* op, int blk, int64_t* base, int64_t* per_peer, int* col0, int* width);
+int fh_ga_slab_kblock_stage(fh_ga* op, int stage, int blk, double* p, const double* r, int pupdate, double* y);
 /* one pipeline step with the CG fusions of fh_cg_steps (p = r + beta p in S1 when pupdate, <p,y> in S5):
  * plain stages 1..5 without fh_ga_slab_direct; with it stage 1 = S1+S2 of `chunk` -> bufA,
  * 3 = S3 on bufB, 4 = S4+S5 of `chunk` from bufA.  Replaces one Afun(P) of general/solver.py:125 */

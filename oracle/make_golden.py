@@ -427,7 +427,72 @@ def gen_potential():
     print('potential.npz: %d arrays' % len(out))
 
 
+# ----------------------------------------------------------------------------- 7. material coefficients
+def _conf_json(conf):
+    import json
+    out = {}
+    for k, v in conf.items():
+        if k in ('inclusions',):
+            out[k] = list(v)
+        elif k in ('positions', 'params', 'vals'):
+            out[k] = [x if isinstance(x, str) else np.asarray(x).tolist() for x in v]
+        elif k in ('Y', 'P'):
+            out[k] = np.asarray(v).tolist()
+        else:
+            out[k] = v
+    return json.dumps(out)
+
+
+def gen_materials():
+    """Material.get_A_GaNi / get_A_Ga (ffthompy/materials.py:54-124) of the UNMODIFIED reference for every material of
+    the example input files plus shifted / anisotropic / 3-D ball / even-grid variants; the configuration travels as
+    JSON next to the arrays."""
+    os.chdir(REF)
+    out, names = {}, []
+    confs = []
+    for f in ['examples/scalar/scalar_2d.py', 'examples/scalar/scalar_3d.py', 'examples/elasticity/linelas_3d.py']:
+        conf = quiet(import_file, f)
+        for mname, m in conf.materials.items():
+            if 'fun' in m or 'inclusions' not in m:
+                continue
+            confs.append((os.path.basename(f).split('.')[0]+'_'+mname, m, np.array(conf.N)))
+    d2, d3 = np.ones(2), np.ones(3)
+    confs += [
+        ('shifted_square', {'inclusions': ['square', 'otherwise'], 'positions': [np.array([0.2, -0.15]), ''],
+                            'params': [np.array([0.5, 0.3]), ''], 'vals': [np.array([[5., 1.], [1., 3.]]), np.eye(2)],
+                            'Y': d2, 'order': None}, np.array([7, 6])),
+        ('two_inclusions', {'inclusions': ['ball', 'square', 'otherwise'], 'positions': [np.array([0.25, 0.25]), np.array([-0.25, -0.2]), ''],
+                            'params': [0.3, np.array([0.3, 0.2]), ''], 'vals': [7*np.eye(2), 3*np.eye(2), np.eye(2)],
+                            'Y': d2, 'order': None}, np.array([9, 10])),
+        ('ball_3d', {'inclusions': ['ball', 'otherwise'], 'positions': [np.zeros(3), ''], 'params': [0.7, ''],
+                     'vals': [11*np.eye(3), np.eye(3)], 'Y': d3, 'order': None}, np.array([6, 5, 7])),
+        ('pyramid_3d', {'inclusions': ['pyramid', 'all'], 'positions': [np.zeros(3), ''], 'params': [0.8*np.ones(3), ''],
+                        'vals': [10.*np.eye(3), np.eye(3)], 'Y': d3, 'order': None}, np.array([5, 6, 5])),
+        ('rect_cell', {'inclusions': ['square', 'otherwise'], 'positions': [np.zeros(2), ''], 'params': [np.array([1.0, 0.4]), ''],
+                       'vals': [11*np.eye(2), np.eye(2)], 'Y': np.array([2., 1.]), 'order': None}, np.array([8, 5])),
+    ]
+    for tag, m, N in confs:
+        m = dict(m)
+        mat = Material(m)
+        Nbar = 2*N-1
+        names.append(tag)
+        out[tag+'_conf'] = np.array(_conf_json(m))
+        out[tag+'_N'] = N
+        for pd in ('primal', 'dual'):
+            out['%s_GaNi_%s' % (tag, pd)] = quiet(mat.get_A_GaNi, N, pd).val
+            out['%s_Ga_None_%s' % (tag, pd)] = quiet(mat.get_A_Ga, Nbar, pd, None).val
+            for order in (0, 1):
+                for Pn, P in (('N', N), ('2N', 2*N), ('3', 3*np.ones(N.size, dtype=int))):
+                    out['%s_Ga_o%d_P%s_%s' % (tag, order, Pn, pd)] = quiet(mat.get_A_Ga, Nbar, pd, order, P).val
+    out['names'] = np.array(names)
+    np.savez_compressed(os.path.join(OUT, 'materials.npz'), **out)
+    print('materials.npz: %d arrays, %d materials' % (len(out), len(names)))
+
+
 if __name__ == '__main__':
+    if '--materials' in sys.argv:
+        gen_materials()
+        sys.exit(0)
     if '--potential' in sys.argv:
         gen_potential()
         sys.exit(0)
@@ -440,4 +505,5 @@ if __name__ == '__main__':
     gen_examples()
     gen_round2()
     gen_potential()
+    gen_materials()
     os.system('ls -la %s' % OUT)

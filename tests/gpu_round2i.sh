@@ -1,0 +1,6 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_materials.py -q --timeout 600 -x > gpurun_out/r2i_pytest_materials.log 2>&1; tail -n 15 gpurun_out/r2i_pytest_materials.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 1 --master-addr 127.0.0.1 --master-port 29533"
+timeout 900 $TR tests/slab_check.py > gpurun_out/r2i_slab_check1.log 2>&1
+grep -c " ok" gpurun_out/r2i_slab_check1.log; grep "FAIL\|Error\|error" gpurun_out/r2i_slab_check1.log | head -5

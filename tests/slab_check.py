@@ -49,12 +49,12 @@ def main():
         E[0] = 1.
         B = Afo(-E)
         xo, io = O.cg(Afo, B, np.zeros_like(B), 1e-6, 1000, N)
-        for mode in ('packed', 'direct', 'direct1', 'peer', 'push') + (('p2p',) if world > 1 else ()):
+        for mode in ('packed', 'direct', 'direct1', 'peer', 'push', 'kblock') + (('p2p',) if world > 1 else ()):
             try:
                 op = SlabGA(dev.upload(Aval[:, :, sl]), G1h+G1s, N, exchange=mode.rstrip('1'),
                             nchunk=(1 if mode == 'direct1' else None))
             except Exception as e:
-                if 'not in the' not in str(e) and 'cannot run' not in str(e) and 'push variant' not in str(e):
+                if 'not in the' not in str(e) and 'cannot run' not in str(e) and 'push variant' not in str(e) and 'column-block variant' not in str(e):
                     raise
                 if rank == 0:
                     print('N=%s world=%d %s: exchange kernels do not cover this grid' % (N, world, mode))
@@ -129,7 +129,7 @@ def main():
                   '%.3e voxel-DOF/s, %.1f%% of the aggregate HBM roofline; NVLink %.2f GB sent per GPU per iteration'
                   % (op.mode, op.nchunk, kind, n, world, per*1e3, 1./per, D*nvox/per,
                      100*rec['hbm_roofline_frac'], nv/1e9), flush=True)
-        if '--profile' in sys.argv and op.mode in ('peer', 'push', 'p2p', 'direct'):
+        if '--profile' in sys.argv and op.mode in ('peer', 'push', 'kblock', 'p2p', 'direct'):
             xp = dev.zeros((D, lay.n0l)+N[1:])
             xp.normal_()
             marks = op.profile_apply(xp)

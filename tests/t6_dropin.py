@@ -1,8 +1,8 @@
 """T6 (SURVEY section 4 / VERDICT round 1 task 1): the reference's OWN integration suite — the 12 example problems of
 run_unittests.py:29-67 through `Problem.calculate()`, plus tutorials 02-04 — executed UNMODIFIED from the copy under
 baseline/_ref with `ffthompy_b200.install()` active, i.e. ffthompy.tensors / .projections / .general.solver /
-.general.solver_pp / .trigpol are this package's device-backed modules while applications.py, materials.py,
-postprocess.py and problem.py are the reference's files.  Checked against the reference's pickled goldens
+.general.solver_pp / .trigpol / .materials / .postprocess are this package's device-backed modules while
+applications.py and problem.py (the callers) are the reference's files.  Checked against the reference's pickled goldens
 (test_results/python3/*): homogenised matrices to 1e-9 (the reference's own bar, run_unittests.py:62) and CG
 iteration counts equal.
 
@@ -67,7 +67,8 @@ def run(log=print):
     from ffthompy.problem import Problem, import_file
     import ffthompy.applications as apps
     assert apps.Tensor.__module__.startswith('ffthompy_b200') and apps.linear_solver.__module__.startswith('ffthompy_b200')
-    assert apps.Material.__module__ == 'ffthompy.materials'      # the reference's own callers
+    assert apps.Material.__module__.startswith('ffthompy_b200') and apps.postprocess.__module__.startswith('ffthompy_b200')
+    assert apps.scalar.__module__ == 'ffthompy.applications'     # the reference's own callers
     os.chdir(REF)
     n0 = device.launch_count()
     worst, fails = 0., []
