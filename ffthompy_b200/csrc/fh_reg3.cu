@@ -71,12 +71,10 @@ int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
     return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass last-axis kernel for N=%d D=%d TRW=%d", N, D, trw);
 }
 
-template <int N, int T, int KIND, int DIM>
-static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
-                  const int64_t* rowoff = nullptr, int64_t cstride = 0, cplx* dout = nullptr,
-                  const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0, int kcol0 = 0) {
+template <int N, int T, int KIND, int DIM, int NT>
+static int mid_KD_NT(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch, const int64_t* rowoff,
+                     int64_t cstride, cplx* dout, const int64_t* rowoff_out, int64_t cstride_out, int kcol0) {
     constexpr int D = (KIND == FH_GREEN_SCALAR) ? DIM : DIM * (DIM + 1) / 2;
-    constexpr int NT = 768;
     const size_t smem = (size_t)D * (N + N / 8) * T * sizeof(cplx);
     int rc;
     if ((rc = reg3_smem_attr(k_mid_green_reg3<N, T, KIND, DIM, NT>, smem))) return rc;
@@ -84,6 +82,19 @@ static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner,
         data, tw, g, inner, nh, pitch, rowoff, rowoff ? cstride : (int64_t)N * inner, dout, rowoff_out, cstride_out, kcol0);
     FH_LAUNCH_CHECK();
     return FH_OK;
+}
+// threads per CTA of the axis-0 kernel: 768 (85 registers, the Green stage spills ~200 B) or 512 (128 registers, no
+// spill, three rounds per pass instead of two); FH_REG3_NT picks, the default is what measured faster on B200
+template <int N, int T, int KIND, int DIM>
+static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
+                  const int64_t* rowoff = nullptr, int64_t cstride = 0, cplx* dout = nullptr,
+                  const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0, int kcol0 = 0) {
+    static const int nt = reg3_env("FH_REG3_NT", 768);
+    if (nt == 512)
+        return mid_KD_NT<N, T, KIND, DIM, 512>(data, tw, g, inner, nh, pitch, rowoff, cstride, dout, rowoff_out, cstride_out, kcol0);
+    if (nt == 384)
+        return mid_KD_NT<N, T, KIND, DIM, 384>(data, tw, g, inner, nh, pitch, rowoff, cstride, dout, rowoff_out, cstride_out, kcol0);
+    return mid_KD_NT<N, T, KIND, DIM, 768>(data, tw, g, inner, nh, pitch, rowoff, cstride, dout, rowoff_out, cstride_out, kcol0);
 }
 // push mode (fh_slab2.cu): natural y-slab input `data`, output rows scattered through rowoff_out into `dout`
 int fh_reg3_mid_green_push(int N, int kind, cplx* data, cplx* dout, const cplx* tw, const GreenDesc& g, int64_t inner, int nh,

@@ -116,7 +116,39 @@ def direct_offsets(layout, D, P, nchunk):
     return off1, off0, n0c*inner, inner, n0c*inner, G*D*n0c*inner
 
 
-def best_exchange(A_local, G, N, group=None, modes=('push', 'p2p'), reps=3):
+def kblock_offsets(layout, D, P, nblk):
+    """Layout of the k2-block exchange buffers (mirrors fh_ga_slab_kblock in csrc/fh_slab2.cu): the pitch/8 column
+    tiles are dealt to `nblk` blocks; block b holds [G][D][n0l][n1l][w_b] elements at offset base[b].
+    Returns a list of (col0, width, base, per_peer, off1[N1], off0[N0]) per block:
+      x-slab side, panel (c, i0l), row k1, block column t:   base + c*n0l*n1l*w + i0l*n1l*w + off1[k1] + t
+      y-slab side, component c, global plane i0, ii = k1l*w + t:   base + off0[i0] + c*n0l*n1l*w + ii"""
+    G, n0l, n1l = layout.world, layout.n0l, layout.n1l
+    ntile = P//8
+    out, c0 = [], 0
+    for b in range(nblk):
+        w = 8*(ntile//nblk+(1 if b < ntile % nblk else 0))
+        inner = n1l*w
+        k1 = np.arange(layout.N[1])
+        i0 = np.arange(layout.N[0])
+        out.append((c0, w, D*n0l*layout.N[1]*c0, D*n0l*inner, (k1//n1l)*D*n0l*inner+(k1 % n1l)*w,
+                    ((i0//n0l)*D*n0l+(i0 % n0l))*inner))
+        c0 += w
+    return out
+
+
+def push_offsets(layout, P):
+    """Row offsets of the push exchange (mirrors fh_ga_slab_push), in elements and WITHOUT the peer-pointer deltas:
+    off1[k1]: S2 output row k1 of panel (c, i0l) lands in rank k1//n1l's y-slab spectrum [D][N0][n1l][P] at
+              c*N0*n1l*P + i0l*n1l*P + off1[k1];
+    off0[i0]: S3 output row i0 of component c lands in rank i0//n0l's x-slab spectrum [D][n0l][N1][P] at
+              c*n0l*N1*P + off0[i0] + ii."""
+    n0l, n1l, r = layout.n0l, layout.n1l, layout.rank
+    k1 = np.arange(layout.N[1])
+    i0 = np.arange(layout.N[0])
+    return (r*n0l*n1l+(k1 % n1l))*P, ((i0 % n0l)*layout.N[1]+r*n1l)*P
+
+
+def best_exchange(A_local, G, N, group=None, modes=('kblock', 'p2p'), reps=3):
     """Measure, don't guess: build the operator with each exchange mode in `modes`, time `reps` applications on
     the device (max over ranks, so every rank takes the same decision) and return (name, {name: ms}).  Modes
     whose kernels or memory mappings are not available here are skipped; which one wins depends on grid size
@@ -231,7 +263,7 @@ class SlabGA(object):
                 self.mode = 'push'
                 # x-plane chunks of S1 | S2: S2 (NVLink stores) of chunk j runs on a side stream under S1 (HBM) of j+1
                 import os
-                want = int(nchunk) if nchunk else int(os.environ.get('FH_PUSH_CHUNKS', '4'))
+                want = int(nchunk) if nchunk else int(os.environ.get('FH_PUSH_CHUNKS', '1'))   # measured on 2 x B200: chunking S1|S2 does not pay (profiles/r02_*)
                 need = 8 if (lay.N[2] & (lay.N[2]-1)) == 0 else 24      # rows per S1 launch: a multiple of its rows per CTA
                 rows_ok = lambda J: lay.n0l % J == 0 and ((lay.n0l//J)*lay.N[1]) % need == 0   # noqa: E731
                 self.nchunk = max([J for J in (8, 4, 2, 1) if J <= max(want, 1) and (J == 1 or rows_ok(J))])
@@ -325,7 +357,7 @@ class SlabGA(object):
             xb = dev.zeros((4*nel,))
         self._xb = xb
         bufA, bufB = cview(xb[:2*nel]), cview(xb[2*nel:])
-        J = int(nblk) if nblk else int(os.environ.get('FH_KBLOCKS', '3'))
+        J = int(nblk) if nblk else int(os.environ.get('FH_KBLOCKS', '2'))   # 8 x B200, 512^3: 2 blocks 5.03 ms, 3: 5.22, 4: 5.56
         J = max(1, min(J, P//8, 16))
         rc = lib.fh_ga_slab_kblock(self.handle, world, J, dev.ptr(bufA), dev.ptr(bufB))
         if not self._agree(rc == 0):
@@ -346,19 +378,36 @@ class SlabGA(object):
             else:
                 self.kpeerA.append(bufA)
                 self.kpeerB.append(bufB)
-        self.kstreams = (torch.cuda.Stream(), torch.cuda.Stream())   # forward / backward copy streams
+        # copy streams per direction (FH_KBLOCK_STREAMS, default 1).  Measured on 8 x B200 at 512^3: one stream per peer
+        # (7 copy engines side by side) is SLOWER than one stream for all peers, 5.92 vs 5.03 ms per CG iteration
+        # (profiles/r02_slab_8gpu_*): the concurrent copies take HBM and NVLink bandwidth from the running kernels.
+        npeer = max(1, min(max(1, world-1), int(os.environ.get('FH_KBLOCK_STREAMS', '1'))))
+        self.kstreams = ([torch.cuda.Stream() for _ in range(npeer)], [torch.cuda.Stream() for _ in range(npeer)])
 
     def _kstage(self, s, blk, p, r, pupdate, y):
         self.L.check(self.dev.lib().fh_ga_slab_kblock_stage(self.handle, s, int(blk), self.dev.ptr(p),
                                                             self.dev.ptr(r) if r is not None else None,
                                                             int(pupdate), self.dev.ptr(y)))
 
-    def _kpush(self, peers, src, blk):
-        """block `blk` of this rank's buffer `src`: piece g -> slot `rank` of block `blk` in peer g's buffer"""
+    def _kpush(self, peers, src, blk, streams, ready):
+        """block `blk` of this rank's buffer `src`: piece g -> slot `rank` of block `blk` in peer g's buffer, the
+        remote pieces spread over the copy streams (`ready`: event the producer kernel recorded); returns with every
+        copy joined into streams[0]"""
+        import torch
         G, me = self.layout.world, self.layout.rank
         base, per = self.kinfo[blk]
-        for g in [(me+k) % G for k in range(1, G)]+[me]:
-            peers[g][base+me*per:base+(me+1)*per].copy_(src[base+g*per:base+(g+1)*per], non_blocking=True)
+        for st in streams:
+            st.wait_event(ready)
+        for k in range(1, G):
+            g = (me+k) % G
+            with torch.cuda.stream(streams[(k-1) % len(streams)]):
+                peers[g][base+me*per:base+(me+1)*per].copy_(src[base+g*per:base+(g+1)*per], non_blocking=True)
+        with torch.cuda.stream(streams[0]):      # the local piece, then the join
+            peers[me][base+me*per:base+(me+1)*per].copy_(src[base+me*per:base+(me+1)*per], non_blocking=True)
+        for st in streams[1:]:
+            e = torch.cuda.Event()
+            e.record(st)
+            streams[0].wait_event(e)
 
     def _apply_kblock(self, x, y, r, pupdate):
         import torch
@@ -372,13 +421,12 @@ class SlabGA(object):
             self._kstage(2, b, x, r, 0, y)
             ev = torch.cuda.Event()
             ev.record(main)
-            csF.wait_event(ev)
-            with torch.cuda.stream(csF):
-                self._kpush(self.kpeerB, self.kbufA, b)
+            self._kpush(self.kpeerB, self.kbufA, b, csF, ev)
+            with torch.cuda.stream(csF[0]):
                 if multi:
                     self.xsymm.barrier(channel=0)          # block b of every rank has landed everywhere
                 e = torch.cuda.Event()
-                e.record(csF)
+                e.record(csF[0])
                 landed.append(e)
         back = []
         for b in range(J):
@@ -386,13 +434,12 @@ class SlabGA(object):
             self._kstage(3, b, x, r, 0, y)
             ev = torch.cuda.Event()
             ev.record(main)
-            csB.wait_event(ev)
-            with torch.cuda.stream(csB):
-                self._kpush(self.kpeerA, self.kbufB, b)
+            self._kpush(self.kpeerA, self.kbufB, b, csB, ev)
+            with torch.cuda.stream(csB[0]):
                 if multi:
                     self.xsymm.barrier(channel=1)
                 e = torch.cuda.Event()
-                e.record(csB)
+                e.record(csB[0])
                 back.append(e)
         for b in range(J):
             main.wait_event(back[b])
@@ -663,12 +710,15 @@ class SlabGA(object):
     def cg_begin(self, B, x0):
         """initial residual of general/solver.py:80-100 (one operator application on x0); returns the
         CG state (x, vecs, r, p, Ap, have_beta, norm_res) that `cg_steps` advances."""
-        from . import ops
         L, lib, dev = self.L, self.dev.lib(), self.dev
         n = self.D*self.nloc
         shape = tuple(x0.shape)
-        x = ops.clone(x0)
-        vecs = dev.empty((3*n,))
+        # the CG vectors live in buffers owned by the operator: the CUDA graph of the iteration (captured once, see
+        # _capture_iteration) holds their addresses and serves every later solve on this operator
+        if getattr(self, '_cgbuf', None) is None:
+            self._cgbuf = (dev.empty(shape), dev.empty((3*n,)))
+        x, vecs = self._cgbuf
+        x.copy_(x0)
         r, p, Ap = (vecs[i*n:(i+1)*n].view(shape) for i in range(3))
         self.apply(x, Ap)
         L.check(lib.fh_cgd_init(self.handle, dev.ptr(B), dev.ptr(vecs)))
@@ -676,18 +726,70 @@ class SlabGA(object):
         return {'x': x, 'vecs': vecs, 'r': r, 'p': p, 'Ap': Ap, 'have_beta': 0, 'norm_res': norm_res, 'kit': 0,
                 'hist': [norm_res]}
 
+    def _capture_iteration(self, st):
+        """One steady-state CG iteration (deferred x update pending, p = r + beta p folded into S1) as a CUDA graph:
+        operator application with its exchange on the copy streams, both scalar reductions with their all-reduces,
+        and the residual update.  Replaying it costs one launch instead of ~100 host calls (8 GPUs, 3 blocks: 48 copies,
+        14 kernels, 12 events, 6 barriers) — the host was the bottleneck of the chunked exchanges (profiles/r02_*)."""
+        import torch
+        import torch.distributed as dist
+        L, lib, dev = self.L, self.dev.lib(), self.dev
+        main = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(main)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            with torch.cuda.graph(graph, stream=side, capture_error_mode='thread_local'):
+                cur = torch.cuda.current_stream()
+                L.check(lib.fh_set_stream(C.c_void_p(cur.cuda_stream)))
+                L.check(lib.fh_ga_set_xacc(self.handle, dev.ptr(st['x'])))
+                self.apply(st['p'], st['Ap'], r=st['r'], pupdate=1)
+                L.check(lib.fh_ga_set_xacc(self.handle, None))
+                L.check(lib.fh_cgd_local_sum(self.handle, dev.ptr(self.sums)))
+                if self.layout.world > 1:
+                    dist.all_reduce(self.sums[:1], op=dist.ReduceOp.SUM, group=self.group)
+                L.check(lib.fh_cgd_scal(self.handle, dev.ptr(self.sums), 1, None))
+                L.check(lib.fh_cgd_update_r(self.handle, dev.ptr(st['vecs'])))
+                L.check(lib.fh_cgd_local_sum(self.handle, dev.ptr(self.sums)))
+                if self.layout.world > 1:
+                    dist.all_reduce(self.sums[:1], op=dist.ReduceOp.SUM, group=self.group)
+        except Exception:
+            graph = None
+        finally:
+            L.check(lib.fh_ga_set_xacc(self.handle, None))
+            L.check(lib.fh_set_stream(C.c_void_p(main.cuda_stream)))
+        return graph
+
     def cg_steps(self, st, tol, nsteps):
         """at most `nsteps` further CG iterations (stops early once ||r|| <= tol, the reference's absolute
         test); alpha, beta, rr stay on the device, the host reads only ||r|| (8 bytes) per iteration.
         Returns the number of iterations done."""
+        import os
         L, lib, dev = self.L, self.dev.lib(), self.dev
         done = 0
         # deferred x update (as in fh_cg_steps): x += alpha p of iteration k is applied by S1 of iteration k+1,
         # which has p in registers anyway (one field read less per iteration), and flushed before returning
         defer = bool(lib.fh_ga_can_defer_x(self.handle))
-        pending = False
+        want_graph = defer and self.mode in ('kblock', 'p2p', 'push', 'peer') and os.environ.get('FH_SLAB_GRAPH', '1') != '0'
+        pending = st.get('pending', False)
         while st['norm_res'] > tol and done < nsteps:
             done += 1
+            if want_graph and pending and st['have_beta']:
+                if 'graph' not in st:
+                    key = (st['x'].data_ptr(), st['vecs'].data_ptr())
+                    if getattr(self, '_graph', (None, None))[0] != key:
+                        g = self._capture_iteration(st)       # every rank captures: the capture contains collectives
+                        if not self._agree(g is not None):
+                            g = None
+                        self._graph = (key, g)
+                    st['graph'] = self._graph[1]
+                if st['graph'] is not None:
+                    st['graph'].replay()
+                    if self.layout.world > 1:
+                        self.exchanged_bytes += 2*self.spec.numel()*16*(self.layout.world-1)//self.layout.world
+                    st['norm_res'] = self._scal_only(2)
+                    st['hist'].append(st['norm_res'])
+                    continue
             if pending:
                 L.check(lib.fh_ga_set_xacc(self.handle, dev.ptr(st['x'])))
             try:
@@ -705,15 +807,23 @@ class SlabGA(object):
             st['norm_res'] = self._global_scalar(2, True)
             st['have_beta'] = 1
             st['hist'].append(st['norm_res'])
-        if pending:
+        if pending and st.get('flush', True):
             L.check(lib.fh_cgd_xflush(self.handle, dev.ptr(st['x']), dev.ptr(st['vecs'])))
+            pending = False
+        st['pending'] = pending
         st['kit'] += done
         return done
+
+    def _scal_only(self, mode):
+        """the device scalars from the already all-reduced sum + the 8-byte read-back of ||r||"""
+        norm = C.c_double()
+        self.L.check(self.dev.lib().fh_cgd_scal(self.handle, self.dev.ptr(self.sums), mode, C.byref(norm)))
+        return norm.value
 
     def cg(self, B, x0, tol=1e-6, maxiter=1000):
         """general/solver.py:80-139 on the slab.  Returns x (device, local slab), info."""
         st = self.cg_begin(B, x0)
         self.cg_steps(st, tol, maxiter)
         kit = st['kit']
-        return st['x'], {'kit': kit, 'norm_res': st['norm_res'] if kit > 0 else 0,
+        return st['x'].clone(), {'kit': kit, 'norm_res': st['norm_res'] if kit > 0 else 0,
                          'norm_res_log': np.array(st['hist'])}

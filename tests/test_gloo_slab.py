@@ -29,7 +29,8 @@ def _worker(rank, world, port, N, D, kind, q):
         sys.path.insert(0, ROOT)
         sys.path.insert(0, os.path.join(ROOT, 'oracle'))
         import ffthom_oracle as O
-        from ffthompy_b200.slab import SlabLayout, exchange_fwd, exchange_bwd, allreduce_sum, direct_offsets
+        from ffthompy_b200.slab import (SlabLayout, exchange_fwd, exchange_bwd, allreduce_sum, direct_offsets,
+                                        kblock_offsets, push_offsets)
         dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
         lay = SlabLayout(N, world, rank)
         rng = np.random.default_rng(11)
@@ -89,6 +90,50 @@ def _worker(rank, world, port, N, D, kind, q):
             for j in range(J):
                 dist.all_to_all_single(tA[j], tB[j])
             assert np.array_equal(tA.numpy().reshape(-1)[idxA], specp[cc, jj*n0c+ii, kk, tt])
+        # k2-block exchange buffers (fh_ga_slab_kblock): scatter as S2 writes block b, one all_to_all_single per block,
+        # gather as S3 reads it == the columns of block b of the packed exchange; and back
+        for nblk in [j for j in (1, 2, 3) if j <= P//8]:
+            n0l, n1l = lay.n0l, lay.n1l
+            for c0, w, base, per, off1, off0 in kblock_offsets(lay, D, P, nblk):
+                bufA = np.zeros(world*per, dtype=complex)
+                cc, ii, kk, tt = np.meshgrid(np.arange(D), np.arange(n0l), np.arange(N[1]), np.arange(w), indexing='ij')
+                idxA = cc*n0l*n1l*w+ii*n1l*w+off1[kk]+tt
+                assert np.unique(idxA).size == idxA.size == bufA.size
+                bufA[idxA] = specp[cc, ii, kk, c0+tt]
+                tA, tB = torch.from_numpy(bufA), torch.zeros(world*per, dtype=torch.complex128)
+                dist.all_to_all_single(tB, tA)                  # piece g of `per` elements -> slot `rank` on peer g
+                c3, i3, k3, t3 = np.meshgrid(np.arange(D), np.arange(N[0]), np.arange(n1l), np.arange(w), indexing='ij')
+                idxB = off0[i3]+c3*n0l*n1l*w+k3*w+t3
+                assert np.unique(idxB).size == idxB.size == bufA.size
+                assert np.array_equal(tB.numpy()[idxB], specT[..., c0:c0+w])
+                dist.all_to_all_single(tA, tB)
+                assert np.array_equal(tA.numpy()[idxA], specp[cc, ii, kk, c0+tt])
+            assert base == D*n0l*N[1]*c0 and c0+w == P
+        # push exchange (fh_ga_slab_push): every rank STORES its S2 rows into the owners' y-slab spectra.  Emulated with
+        # an all_gather of the x-slab spectra: what the stores of all ranks leave in this rank's y-slab spectrum
+        allspec = [torch.zeros_like(torch.from_numpy(specp)) for _ in range(world)]
+        dist.all_gather(allspec, torch.from_numpy(specp))
+        mineT = np.zeros(D*N[0]*lay.n1l*P, dtype=complex)
+        for src in range(world):
+            lsrc = SlabLayout(N, world, src)
+            off1, _ = push_offsets(lsrc, P)
+            rows = np.arange(lay.n1_off, lay.n1_off+lay.n1l)               # the k1 rows this rank owns
+            cc, ii, kk, tt = np.meshgrid(np.arange(D), np.arange(lsrc.n0l), rows, np.arange(P), indexing='ij')
+            dst = cc*N[0]*lay.n1l*P+ii*lay.n1l*P+off1[kk]+tt
+            mineT[dst] = allspec[src].numpy()[cc, ii, kk, tt]
+        assert np.array_equal(mineT.reshape(D, N[0], lay.n1l, P), specT)
+        # ... and S3's stores back into the owners' x-slab spectra
+        allT = [torch.zeros_like(torch.from_numpy(backp)) for _ in range(world)]
+        dist.all_gather(allT, torch.from_numpy(backp))
+        mine = np.zeros(D*lay.n0l*N[1]*P, dtype=complex)
+        for src in range(world):
+            lsrc = SlabLayout(N, world, src)
+            _, off0 = push_offsets(lsrc, P)
+            planes = np.arange(lay.n0_off, lay.n0_off+lay.n0l)
+            cc, ii, kk, tt = np.meshgrid(np.arange(D), planes, np.arange(lsrc.n1l), np.arange(P), indexing='ij')
+            dst = cc*lay.n0l*N[1]*P+off0[ii]+kk*P+tt
+            mine[dst] = allT[src].numpy()[cc, ii, kk, tt]
+        assert np.array_equal(mine.reshape(D, lay.n0l, N[1], P), back)
         tot = allreduce_sum(np.sum(x_loc*ref[:, sl]), torch.device('cpu'))
         err_dot = abs(tot-np.sum(x*ref))/abs(np.sum(x*ref))
         q.put((rank, float(err), float(err_rt), float(err_dot)))
