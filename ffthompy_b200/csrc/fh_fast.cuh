@@ -280,21 +280,25 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     }
     s1_sigma_phase<N, D, TRW, ALAY, NT>(A, phase, slut, lutc, p, r, beta, pupdate, row0, n,
                                         [&](int L, int i2, double s0, double s1) {
+                                            // plain (unpadded) positions, one 16-byte store: the linear phases of this
+                                            // kernel (this one, pass-1 loads, the final separation) use the plain
+                                            // layout, only the stride-16 scatter / gather between the two radix passes
+                                            // the padded one (ncu r01d: 23 % excess shared wavefronts came from linear
+                                            // 8-byte accesses crossing the one-per-16 padding)
                                             double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
-                                            dst[pidx(i2)] = s0;
-                                            dst[pidx(i2 + 1)] = s1;
+                                            *reinterpret_cast<double2*>(dst + i2) = make_double2(s0, s1);
                                         },
                                         xacc, alpha);
     __syncthreads();
     const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
     double* lre = zre + pr * NPAD;
     double* lim = zim + pr * NPAD;
-    // pass 1 (rows j + r*R2 -> rows j*R1 + q): not in place, so read / barrier / write
+    // pass 1 (rows j + r*R2, plain -> rows j*R1 + q, padded): not in place, so read / barrier / write
     {
         cplx v[R1];
         if (j < R2) {
 #pragma unroll
-            for (int rr = 0; rr < R1; ++rr) v[rr] = make_double2(lre[pidx(j + rr * R2)], lim[pidx(j + rr * R2)]);
+            for (int rr = 0; rr < R1; ++rr) v[rr] = make_double2(lre[j + rr * R2], lim[j + rr * R2]);
             Bfly<R1, false>::run(v);
         }
         __syncthreads();
@@ -307,18 +311,24 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
         }
     }
     __syncthreads();
-    // pass 2, in place
-    if (j < R1) {
+    // pass 2: padded -> plain (the 16 threads of a line sit in one warp: a warp barrier separates the gather from
+    // the writes that reuse the line's storage in the other layout)
+    {
         cplx v[R2];
+        if (j < R1) {
 #pragma unroll
-        for (int rr = 0; rr < R2; ++rr) v[rr] = make_double2(lre[pidx(j + rr * R1)], lim[pidx(j + rr * R1)]);
+            for (int rr = 0; rr < R2; ++rr) v[rr] = make_double2(lre[pidx(j + rr * R1)], lim[pidx(j + rr * R1)]);
 #pragma unroll
-        for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, false));
-        Bfly<R2, false>::run(v);
+            for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, false));
+            Bfly<R2, false>::run(v);
+        }
+        __syncwarp();
+        if (j < R1) {
 #pragma unroll
-        for (int q = 0; q < R2; ++q) {
-            lre[pidx(j + q * R1)] = v[q].x;
-            lim[pidx(j + q * R1)] = v[q].y;
+            for (int q = 0; q < R2; ++q) {
+                lre[j + q * R1] = v[q].x;
+                lim[j + q * R1] = v[q].y;
+            }
         }
     }
     __syncthreads();
@@ -331,8 +341,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
             const double* qre = zre + (L >> 1) * NPAD;
             const double* qim = zim + (L >> 1) * NPAD;
             const int km = (k == 0) ? 0 : N - k;
-            const double ax_ = qre[pidx(k)], ay_ = qim[pidx(k)];
-            const double bx_ = qre[pidx(km)], by_ = qim[pidx(km)];
+            const double ax_ = qre[k], ay_ = qim[k];
+            const double bx_ = qre[km], by_ = qim[km];
             X = (L & 1) ? make_double2(0.5 * (ay_ + by_), -0.5 * (ax_ - bx_))
                         : make_double2(0.5 * (ax_ + bx_), 0.5 * (ay_ - by_));
         }
@@ -386,13 +396,13 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL, MINB)
                 av.y = 0.0;
                 bv.y = 0.0;
             }
-            double* qre = zre + prs[u] * NPAD;
+            double* qre = zre + prs[u] * NPAD;   // plain (unpadded) positions: linear accesses, see k_fwd_last_fast
             double* qim = zim + prs[u] * NPAD;
-            qre[pidx(k)] = av.x - bv.y;
-            qim[pidx(k)] = av.y + bv.x;
+            qre[k] = av.x - bv.y;
+            qim[k] = av.y + bv.x;
             if (k > 0 && 2 * k != N) {
-                qre[pidx(N - k)] = av.x + bv.y;
-                qim[pidx(N - k)] = -av.y + bv.x;
+                qre[N - k] = av.x + bv.y;
+                qim[N - k] = -av.y + bv.x;
             }
         }
     }
@@ -400,18 +410,24 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL, MINB)
     const int j = threadIdx.x % TPL, pr = threadIdx.x / TPL;
     double* lre = zre + pr * NPAD;
     double* lim = zim + pr * NPAD;
-    // inverse of pass 2, in place
-    if (j < R1) {
+    // inverse of pass 2: plain -> padded (warp barrier between the gather and the writes in the other layout: the
+    // TPL threads of a line sit in one warp)
+    {
         cplx v[R2];
+        if (j < R1) {
 #pragma unroll
-        for (int q = 0; q < R2; ++q) v[q] = make_double2(lre[pidx(j + q * R1)], lim[pidx(j + q * R1)]);
-        Bfly<R2, true>::run(v);
+            for (int q = 0; q < R2; ++q) v[q] = make_double2(lre[j + q * R1], lim[j + q * R1]);
+            Bfly<R2, true>::run(v);
 #pragma unroll
-        for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, true));
+            for (int rr = 1; rr < R2; ++rr) v[rr] = cmul(v[rr], ldtw(tw, rr * j, true));
+        }
+        __syncwarp();
+        if (j < R1) {
 #pragma unroll
-        for (int rr = 0; rr < R2; ++rr) {
-            lre[pidx(j + rr * R1)] = v[rr].x;
-            lim[pidx(j + rr * R1)] = v[rr].y;
+            for (int rr = 0; rr < R2; ++rr) {
+                lre[pidx(j + rr * R1)] = v[rr].x;
+                lim[pidx(j + rr * R1)] = v[rr].y;
+            }
         }
     }
     __syncthreads();

@@ -2,6 +2,7 @@
 // Internal C++ interface (fh_reg3.h) used by the fused operator in fh_fused.cu; nothing here is part of the C ABI.
 #include "fh_reg3.cuh"
 #include "fh_reg3.h"
+#include "fh_mid512.h"
 #include <stdlib.h>
 
 template <typename K>
@@ -89,6 +90,9 @@ template <int N, int T, int KIND, int DIM>
 static int mid_KD(cplx* data, const cplx* tw, const GreenDesc& g, int64_t inner, int nh, int pitch,
                   const int64_t* rowoff = nullptr, int64_t cstride = 0, cplx* dout = nullptr,
                   const int64_t* rowoff_out = nullptr, int64_t cstride_out = 0, int kcol0 = 0) {
+    // N0 = 512 in 3-D: the two-stage 32 x 16 kernel (fh_mid512.cu) unless FH_MID512=0
+    if (N == 512 && DIM == 3 && T == 4 && fh_mid512_on())
+        return fh_mid512_green(KIND, data, tw, g, inner, nh, pitch, rowoff, cstride, dout, rowoff_out, cstride_out, kcol0);
     static const int nt = reg3_env("FH_REG3_NT", 768);
     if (nt == 512)
         return mid_KD_NT<N, T, KIND, DIM, 512>(data, tw, g, inner, nh, pitch, rowoff, cstride, dout, rowoff_out, cstride_out, kcol0);
