@@ -38,6 +38,7 @@ _SIGNATURES = {
     'fh_last_error': (C.c_char_p, []),
     'fh_version': (c_int, []),
     'fh_device_info': (c_int, [p_int, p_int, p_int]),
+    'fh_download': (c_int, [c_vp, c_vp, c_i64]),
     'fh_plan_create': (c_int, [C.POINTER(c_vp), c_int, p_i64]),
     'fh_plan_destroy': (c_int, [c_vp]),
     'fh_plan_factors': (c_int, [c_vp, c_int, p_int, p_int]),

@@ -7,7 +7,7 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ['fh_fft.cu', 'fh_pointwise.cu', 'fh_fused.cu', 'fh_reg3.cu', 'fh_mid2.cu', 'fh_slab2.cu', 'fh_material.cu', 'fh_mid512.cu']
+SOURCES = ['fh_fft.cu', 'fh_pointwise.cu', 'fh_fused.cu', 'fh_reg3.cu', 'fh_mid2.cu', 'fh_slab2.cu', 'fh_material.cu', 'fh_mid512.cu', 'fh_host.cu', 'fh_odd.cu']
 HEADERS = sorted(f for f in os.listdir(HERE) if f.endswith('.cuh') or f.endswith('.h')) + [os.path.join('..', '..', 'include', 'ffthom_b200.h')]
 LIB = os.path.join(PKG, 'libffthom_b200.so')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
@@ -38,7 +38,7 @@ def build(force=False, verbose=False):
         # fh_reg3.cuh (kernel bodies) is included by fh_reg3.cu only; the other units see fh_reg3.h
         # kernel-body headers that only some units include (keeps the 7-minute fh_fused.cu out of their edit cycle)
         private = {'fh_reg3.cuh': ('fh_reg3.cu',), 'fh_mid2.cuh': ('fh_mid2.cu', 'fh_mid512.cu'),
-                   'fh_mid512.h': ('fh_reg3.cu', 'fh_mid512.cu')}
+                   'fh_mid512.h': ('fh_reg3.cu', 'fh_mid512.cu'), 'fh_odd.h': ('fh_fused.cu', 'fh_odd.cu')}
         deps = [h for h in hdrs if os.path.basename(h) not in private or src in private[os.path.basename(h)]]
         if force or _stale(o, [s] + deps):
             jobs.append([NVCC] + FLAGS + ['-c', s, '-o', o])

@@ -18,6 +18,7 @@
 #include "fh_fast.cuh"
 #include "fh_reg3.h"
 #include "fh_mid2.h"
+#include "fh_odd.h"
 #include "../../include/ffthom_b200.h"
 #include <stdlib.h>
 #include <string.h>
@@ -935,6 +936,9 @@ static int ga_create(fh_ga** out, const fh_plan* plan, int D, const double* A, i
     if (op->rt_ok[0] && ((size_t)op->rt[0].npr * D * sizeof(cplx) > (size_t)fh_max_smem_optin() ||
                          ((int64_t)op->n1l * op->pitch) % 4 != 0))
         op->rt_ok[0] = false;
+    // compile-time odd-length family (3-D, whole grid on this GPU): per axis, ahead of the run-time-length kernels
+    for (int a = 0; a < 3; ++a)
+        op->odd_ax[a] = use_fast && fh_odd_on() && d == 3 && !slab && (D == 3 || D == 6) && fh_odd_len(plan->N[a]);
     op->mid_T = env_int("FH_MID_T", 4);
     op->mid_pipe = env_int("FH_MID_PIPE", 1);
     if (op->mid_T != 2 && op->mid_T != 4) op->mid_T = 4;
@@ -1006,15 +1010,18 @@ extern "C" int fh_ga_destroy(fh_ga* op) {
 }
 
 // which kernels an operator uses: bit0 fast last axis, bit1 fast axis 1, bit2 fast axis 0;
-// bits 4-5 coefficient mode (0 full, 1 symmetric, 2 phase table), bits 8.. number of phases
+// bits 4-5 coefficient mode (0 full, 1 symmetric, 2 phase table), bits 8.. number of phases,
+// bits 16-18 run-time-length kernels (last / middle / first axis), bits 20-22 compile-time odd-length kernels
 extern "C" int fh_ga_config(const fh_ga* op, int* flags, int* pitch, int* mid_T) {
     FH_REQUIRE(op, "fh_ga_config: null argument");
     if (flags)
         *flags = (op->fast_last ? 1 : 0) | (op->fast_mid1 ? 2 : 0) | (op->fast_mid0 ? 4 : 0) | (op->a_mode << 4) |
                  (op->nphase << 8) |
-                 ((!op->fast_last && op->rt_ok[op->plan->dim - 1]) ? 1 << 16 : 0) |
-                 ((op->plan->dim == 3 && !op->fast_mid1 && op->rt_ok[1]) ? 1 << 17 : 0) |
-                 ((!op->fast_mid0 && op->rt_ok[0]) ? 1 << 18 : 0);
+                 ((!op->fast_last && !op->odd_ax[op->plan->dim - 1] && op->rt_ok[op->plan->dim - 1]) ? 1 << 16 : 0) |
+                 ((op->plan->dim == 3 && !op->fast_mid1 && !op->odd_ax[1] && op->rt_ok[1]) ? 1 << 17 : 0) |
+                 ((!op->fast_mid0 && !op->odd_ax[0] && op->rt_ok[0]) ? 1 << 18 : 0) |
+                 (op->odd_ax[op->plan->dim - 1] ? 1 << 20 : 0) | ((op->plan->dim == 3 && op->odd_ax[1]) ? 1 << 21 : 0) |
+                 (op->odd_ax[0] ? 1 << 22 : 0);
     if (pitch) *pitch = op->pitch;
     if (mid_T) *mid_T = op->mid_T;
     return FH_OK;
@@ -1183,6 +1190,7 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
     int rc;
     switch (stage) {
         case 1:
+            if (op->odd_ax[d - 1] && !op->row_cnt) return fh_odd_fwd_last(op, x, r, pupdate);
             if (op->fast_last) return launch_fwd_last_fast(op, x, r, pupdate, true);
             if (op->rt_ok[d - 1]) return launch_fwd_last_rt(op, x, r, pupdate);
             if (pupdate) {
@@ -1199,10 +1207,12 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
             return fh_launch_r2c_last(p, op->sigma, op->spec, nlines, op->pitch);
         case 2:
             if (d != 3) return FH_OK;
+            if (op->odd_ax[1]) return fh_odd_c2c(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, false);
             if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, false);
             if (op->rt_ok[1]) return launch_c2c_rt(op, 1, op->spec, (int64_t)D * op->n0l, op->pitch, false);
             return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, false, 1.0);
         case 3:
+            if (op->odd_ax[0]) return fh_odd_mid(op);
             if (op->fast_mid0) {
                 if (op->g.kind == FH_GREEN_SCALAR)
                     return (d == 3) ? launch_mid_fast<FH_GREEN_SCALAR, 3>(op) : launch_mid_fast<FH_GREEN_SCALAR, 2>(op);
@@ -1220,10 +1230,12 @@ static int ga_stage(fh_ga* op, int stage, double* x, const double* r, int pupdat
                             : launch_mid_green_generic<FH_GREEN_ELASTIC, 2>(op);
         case 4:
             if (d != 3) return FH_OK;
+            if (op->odd_ax[1]) return fh_odd_c2c(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, true);
             if (op->fast_mid1) return launch_c2c_fast(p->N[1], p->ax[1].tw, op->spec, (int64_t)D * op->n0l, op->pitch, true);
             if (op->rt_ok[1]) return launch_c2c_rt(op, 1, op->spec, (int64_t)D * op->n0l, op->pitch, true);
             return fh_launch_c2c_strided(p->ax[1], op->spec, op->spec, (int64_t)D * op->n0l, op->pitch, true, 1.0);
         case 5:
+            if (op->odd_ax[d - 1] && !op->row_cnt) return fh_odd_inv_last(op, y, dot ? x : NULL, npart);
             if (op->fast_last) return launch_inv_last_fast(op, y, dot ? x : NULL, npart);
             // measured (255^3, 243^3): the generic batched C2R beats the run-time-length one; FH_RT bit 3 opts in
             if (op->rt_ok[d - 1] && (env_int("FH_RT", 7) & 8)) return launch_inv_last_rt(op, y, dot ? x : NULL, npart);

@@ -32,6 +32,7 @@ struct fh_ga {
     // configuration
     bool fast_last, fast_mid1, fast_mid0;
     bool rt_ok[3];   // run-time-length in-place kernels usable on axis a (any N = up to 3 supported radices)
+    bool odd_ax[3];  // compile-time odd-length kernels (fh_odd.cu: 255 = 15 x 17) serve axis a; they take precedence over rt
     RtPlan rt[3];
     int mid_T, trw, mid_pipe;
     int trw_s1;          // rows per CTA of S1 when it differs from trw (0: same)

@@ -71,8 +71,15 @@ def upload(a):
 
 def download(t):
     """device -> host (a fresh pageable array, as `Tensor.val` hands out a new NumPy array every time).  Measured for the
-    0.8 GB solution of a 256^3 elasticity solve: 0.36 s, dominated by the page faults of the fresh destination; a
-    page-locked destination from torch's host allocator was tried and is slower the first time (0.44 s: pinning 0.8 GB)."""
+    0.8 GB solution of a 256^3 elasticity solve with a plain `cudaMemcpy`: 0.36 s, dominated by the page faults of the
+    fresh destination taken by one thread; a page-locked destination from torch's host allocator is slower the first time
+    (0.44 s: pinning 0.8 GB).  Large results therefore go through `fh_download`."""
+    nbytes = t.numel()*t.element_size()
+    if nbytes >= (4 << 20) and t.is_contiguous():
+        # large results: pinned staging ring + parallel first touch of the destination (csrc/fh_host.cu)
+        out = np.empty(tuple(t.shape), dtype=np.complex128 if t.dtype.is_complex else np.float64)
+        L.check(lib().fh_download(C.c_void_p(out.ctypes.data), ptr(t), C.c_int64(nbytes)))
+        return out
     return t.cpu().numpy()
 
 

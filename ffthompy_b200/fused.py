@@ -47,8 +47,10 @@ class FusedGA(object):
         fl, pitch, mt = C.c_int(), C.c_int(), C.c_int()
         L.check(dev.lib().fh_ga_config(self.handle, C.byref(fl), C.byref(pitch), C.byref(mt)))
         f = fl.value
-        fam = lambda fast, rt: 'pow2' if f & fast else ('rt' if f & rt else 'generic')  # noqa: E731
-        return {'last': fam(1, 1 << 16), 'mid1': fam(2, 1 << 17), 'mid0': fam(4, 1 << 18),
+        # 'odd': compile-time two-pass kernels of csrc/fh_odd.cu (255 = 15 x 17); 'rt': run-time-length in-place kernels
+        fam = lambda fast, rt, odd: ('odd' if f & odd else 'pow2' if f & fast else  # noqa: E731
+                                     ('rt' if f & rt else 'generic'))
+        return {'last': fam(1, 1 << 16, 1 << 20), 'mid1': fam(2, 1 << 17, 1 << 21), 'mid0': fam(4, 1 << 18, 1 << 22),
                 'coefficients': ('full', 'symmetric', 'phase')[(f >> 4) & 3], 'nphase': (f >> 8) & 0xff,
                 'pitch': pitch.value}
 

@@ -62,6 +62,10 @@ int fh_sync(void);
 const char* fh_last_error(void);
 int fh_version(void);
 int fh_device_info(int* num_sms, int* smem_optin, int* l2_bytes);
+/* device -> host copy of a result into fresh pageable memory (the new NumPy array `Tensor.val` hands out,
+ * ffthompy/tensors/objects.py:119-121): pinned staging ring + parallel first-touch of the destination; ordered
+ * after the work enqueued on the library stream, complete on return                                          */
+int fh_download(void* dst_host, const void* src_device, int64_t bytes);
 
 /* ---- FFT plan and transforms (ffthompy/tensors/fft.py:39-43; operators.py:14-58) -- */
 int fh_plan_create(fh_plan** plan, int dim, const int64_t* N);

@@ -74,8 +74,9 @@ def test_benchmarked_axis_lengths_against_the_oracle(L, axis, physics, mode, mon
     # a last axis on the generic passes (511) has no fused coefficient multiply: S1 is the plain full-array kernel
     assert cfg['coefficients'] == ('full' if (L == 511 and axis == 2) else mode), cfg
     fam = cfg[('mid0', 'mid1', 'last')[axis]]
-    # 255 = 3*5*17 runs the run-time-length kernels; 511 = 7*73 (73 is no register radix) the generic Stockham passes
-    assert fam == {128: 'pow2', 256: 'pow2', 255: 'rt', 511: 'generic'}[L], cfg
+    # 255 = 15*17 runs the compile-time odd-length kernels (csrc/fh_odd.cu); 511 = 7*73 (73 is no register radix) the
+    # generic Stockham passes
+    assert fam == {128: 'pow2', 256: 'pow2', 255: 'odd', 511: 'generic'}[L], cfg
     Afo = O.GA(Aval, Go, N)
     u = rng.standard_normal((D,)+N)
     ref = Afo(u)
