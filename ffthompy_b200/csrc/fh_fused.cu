@@ -1144,6 +1144,43 @@ __global__ void k_cg_update_r(int64_t n2, double2* __restrict__ r, const double2
     acc = block_sum(acc, red);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
+// the same two kernels for an odd element count (odd grids: prod(N) odd and D odd), where the fields r | p | Ap of
+// `vecs` are only 8-byte aligned: 8-byte accesses, four independent elements per thread and step
+__global__ void k_cg_update_r1(int64_t n, double* __restrict__ r, const double* __restrict__ Ap,
+                               const double* __restrict__ scal, double* __restrict__ part) {
+    __shared__ double red[32];
+    const double alpha = scal[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n; i += 4 * stride) {
+        double rv[4], av[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            rv[u] = r[i + u * stride];
+            av[u] = Ap[i + u * stride];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const double v = rv[u] - alpha * av[u];
+            r[i + u * stride] = v;
+            acc += v * v;
+        }
+    }
+    for (; i < n; i += stride) {
+        const double v = r[i] - alpha * Ap[i];
+        r[i] = v;
+        acc += v * v;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+__global__ void k_cg_xflush1(int64_t n, double* __restrict__ x, const double* __restrict__ p,
+                             const double* __restrict__ scal) {
+    const double alpha = scal[2];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = x[i] + alpha * p[i];
+}
 // x += alpha p  (flush of the deferred update after the last iteration: scal[2] and p are still that iteration's)
 __global__ void k_cg_xflush(int64_t n2, double2* __restrict__ x, const double2* __restrict__ p,
                             const double* __restrict__ scal) {
@@ -1736,8 +1773,8 @@ extern "C" int fh_cg_begin(fh_ga* op, const double* B, double* x, double* vecs, 
 // with <r,r>, two single-CTA scalar kernels, and one 8-byte read-back of the residual norm.
 // Deferred x update (default; FH_XDEFER=0 disables): iteration k leaves x += alpha_k p_k pending; S1 of iteration
 // k+1 applies it before it overwrites p (same expression, same rounding), and the loop flushes the last one
-// before it returns.  Needs an S1 kernel that carries the p update (fast / run-time-length paths) and an
-// even element count.
+// before it returns.  Needs an S1 kernel that carries the p update (fast / run-time-length / odd-length paths); an
+// odd element count takes the 8-byte forms of the two update kernels.
 static int cg_steps_impl(fh_ga* op, double* x, double* vecs, double tol, int64_t nsteps, int64_t* done_host,
                          double* norm_res_host, double* hist_host, int64_t hist_cap) {
     const int64_t n = (int64_t)op->D * op->nloc;
@@ -1751,7 +1788,8 @@ static int cg_steps_impl(fh_ga* op, double* x, double* vecs, double tol, int64_t
     double norm_res = *norm_res_host;
     int64_t done = 0;
     static const int want_defer = env_int("FH_XDEFER", 1);
-    const bool defer = want_defer && n % 2 == 0 && (op->fast_last || op->rt_ok[op->plan->dim - 1]);
+    // (the S1 kernels that apply the pending x += alpha p: two-pass / three-pass, run-time-length and odd-length families)
+    const bool defer = want_defer && (op->fast_last || op->rt_ok[op->plan->dim - 1] || op->odd_ax[op->plan->dim - 1]);
     bool pending = false;  // x += alpha p of the last finished iteration not applied yet
     while (norm_res > tol && done < nsteps) {
         int np = 0;
@@ -1763,7 +1801,10 @@ static int cg_steps_impl(fh_ga* op, double* x, double* vecs, double tol, int64_t
         k_cg_scal<<<1, GA_NT, 0, s>>>(np, op->part, op->scal, inv, 1);
         FH_LAUNCH_CHECK();
         if (defer) {
-            k_cg_update_r<<<g, GA_NT, 0, s>>>(n / 2, (double2*)r, (const double2*)Ap, op->scal, op->part);
+            if (n % 2 == 0)
+                k_cg_update_r<<<g, GA_NT, 0, s>>>(n / 2, (double2*)r, (const double2*)Ap, op->scal, op->part);
+            else
+                k_cg_update_r1<<<g, GA_NT, 0, s>>>(n, r, Ap, op->scal, op->part);
             pending = true;
         } else if (n % 2 == 0) {
             k_cg_update<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (double2*)r, (const double2*)p, (const double2*)Ap,
@@ -1781,7 +1822,10 @@ static int cg_steps_impl(fh_ga* op, double* x, double* vecs, double tol, int64_t
         ++op->kit;
     }
     if (pending) {
-        k_cg_xflush<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (const double2*)p, op->scal);
+        if (n % 2 == 0)
+            k_cg_xflush<<<g, GA_NT, 0, s>>>(n / 2, (double2*)x, (const double2*)p, op->scal);
+        else
+            k_cg_xflush1<<<g, GA_NT, 0, s>>>(n, x, p, op->scal);
         FH_LAUNCH_CHECK();
     }
     *done_host = done;

@@ -37,7 +37,8 @@ bool fh_odd_on() { return odd_env("FH_ODD", 1) != 0; }  // read per operator (fh
 template <typename K>
 static int odd_smem_attr(K kernel, size_t bytes) {
     if (bytes > (size_t)fh_max_smem_optin()) return fh_set_error(FH_ERR_UNSUPPORTED, "odd-length kernel: %zu B shared memory", bytes);
-    if (bytes > 48 * 1024) FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    // (the kernels also hold up to 4.6 KB of static shared memory: opt in well below the 48 KB default limit)
+    if (bytes > 40 * 1024) FH_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return FH_OK;
 }
 
@@ -215,8 +216,8 @@ int fh_odd_mid(fh_ga* op) {
 // NP = NL/2 complex lines as SoA (re plane, im plane), LP = N + 1 doubles apart.  blockDim = NP * TPL.
 // Coefficient layouts as in k_fwd_last_fast: 0 full, 1 upper triangle of the full array, 2 phase table, 3 two phases
 // in the constant bank.
-template <int N, int D, int TRW, int ALAY>
-__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+template <int N, int D, int TRW, int ALAY, int V>
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL, 2)
     k_fwd_last_odd(const double* __restrict__ A, const unsigned char* __restrict__ phase, const double* __restrict__ lut,
                    const Lut2C lutc, int nphase, double* __restrict__ p, const double* __restrict__ r,
                    const double* __restrict__ scal, int pupdate, cplx* __restrict__ spec, const cplx* __restrict__ tw,
@@ -236,54 +237,83 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
         for (int i = threadIdx.x; i < nphase * D * D; i += NT) slut[i] = lut[i];
         __syncthreads();
     }
-    // phase 0: one voxel per thread and step, 8-byte accesses coalesced along the rows
-#pragma unroll 2
-    for (int v = threadIdx.x; v < TRW * N; v += NT) {
-        const int row = v / N, i2 = v - row * N;
-        const bool live = row0 + row < nrows;
-        const int64_t gv = (row0 + row) * N + i2;
-        int ph = 0;
-        if ((ALAY == 2 || ALAY == 3) && live) ph = phase[gv];
-        double pv[D];
+    // phase 0: V voxels per thread and step, 8-byte accesses coalesced along the rows.  All loads of a step are issued
+    // before any is consumed (ncu, round 2: with one or two voxels per step the kernel sat on the load latency, 2.5 TB/s)
+    constexpr int NA = (ALAY == 0) ? D * D : (ALAY == 1 ? D * (D + 1) / 2 : 0);  // coefficient loads per voxel
+    for (int v0 = threadIdx.x; v0 < TRW * N; v0 += V * NT) {
+        double pv[V][D], rv[V][D], xv[V][D], av[V][NA > 0 ? NA : 1];
+        int ph[V], rowv[V], i2v[V];
+        bool live[V];
+        int64_t gvv[V];
 #pragma unroll
-        for (int jj = 0; jj < D; ++jj) {
-            double q = 0.0;
-            if (live) {
-                q = p[(size_t)jj * n + gv];
-                if (pupdate) {
-                    const double rv = r[(size_t)jj * n + gv];
-                    if (xacc) {  // deferred x += alpha p of the previous iteration (solver.py:127)
-                        const double xv = xacc[(size_t)jj * n + gv];
-                        xacc[(size_t)jj * n + gv] = xv + alpha * q;
-                    }
-                    q = rv + beta * q;
-                    p[(size_t)jj * n + gv] = q;
-                }
-            }
-            pv[jj] = q;
+        for (int u = 0; u < V; ++u) {
+            const int v = v0 + u * NT;
+            const int row = v / N;
+            rowv[u] = row;
+            i2v[u] = v - row * N;
+            live[u] = (v < TRW * N) && (row0 + row < nrows);
+            gvv[u] = (row0 + row) * N + i2v[u];
         }
 #pragma unroll
-        for (int i = 0; i < D; ++i) {
-            double s = 0.0;
-            if (live) {
+        for (int u = 0; u < V; ++u) {
+            ph[u] = 0;
+            if ((ALAY == 2 || ALAY == 3) && live[u]) ph[u] = phase[gvv[u]];
 #pragma unroll
-                for (int jj = 0; jj < D; ++jj) {
-                    double a;
-                    if (ALAY == 3) {
-                        a = ph ? lutc.c[1][i * D + jj] : lutc.c[0][i * D + jj];
-                    } else if (ALAY == 2) {
-                        a = slut[ph * D * D + i * D + jj];
-                    } else if (ALAY == 1) {
-                        const int lo = i < jj ? i : jj, hi = i < jj ? jj : i;
-                        a = A[((size_t)lo * D + hi) * n + gv];
-                    } else {
-                        a = A[((size_t)i * D + jj) * n + gv];
-                    }
-                    s += a * pv[jj];
+            for (int jj = 0; jj < D; ++jj) {
+                pv[u][jj] = live[u] ? p[(size_t)jj * n + gvv[u]] : 0.0;
+                if (pupdate) {
+                    rv[u][jj] = live[u] ? r[(size_t)jj * n + gvv[u]] : 0.0;
+                    if (xacc) xv[u][jj] = live[u] ? xacc[(size_t)jj * n + gvv[u]] : 0.0;
                 }
             }
-            const int L = i * TRW + row;
-            ((L & 1) ? zim : zre)[(L >> 1) * LP + i2] = s;
+            if (NA > 0 && live[u]) {
+                if (ALAY == 0) {
+#pragma unroll
+                    for (int e = 0; e < D * D; ++e) av[u][e] = A[(size_t)e * n + gvv[u]];
+                } else {
+                    int e = 0;
+#pragma unroll
+                    for (int lo = 0; lo < D; ++lo)
+#pragma unroll
+                        for (int hi = lo; hi < D; ++hi) av[u][e++] = A[((size_t)lo * D + hi) * n + gvv[u]];
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < V; ++u) {
+            if (v0 + u * NT >= TRW * N) continue;
+            if (pupdate && live[u]) {
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) {
+                    // deferred x += alpha p of the previous iteration (solver.py:127), then p = r + beta p (solver.py:132)
+                    if (xacc) xacc[(size_t)jj * n + gvv[u]] = xv[u][jj] + alpha * pv[u][jj];
+                    pv[u][jj] = rv[u][jj] + beta * pv[u][jj];
+                    p[(size_t)jj * n + gvv[u]] = pv[u][jj];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < D; ++i) {
+                double sg = 0.0;
+                if (live[u]) {
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        double a;
+                        if (ALAY == 3) {
+                            a = ph[u] ? lutc.c[1][i * D + jj] : lutc.c[0][i * D + jj];
+                        } else if (ALAY == 2) {
+                            a = slut[ph[u] * D * D + i * D + jj];
+                        } else if (ALAY == 1) {  // upper triangle, row-major: (lo, hi) -> lo*D - lo(lo-1)/2 + hi - lo
+                            const int lo = i < jj ? i : jj, hi = i < jj ? jj : i;
+                            a = av[u][lo * D - lo * (lo - 1) / 2 + hi - lo];
+                        } else {
+                            a = av[u][i * D + jj];
+                        }
+                        sg += a * pv[u][jj];
+                    }
+                }
+                const int L = i * TRW + rowv[u];
+                ((L & 1) ? zim : zre)[(L >> 1) * LP + i2v[u]] = sg;
+            }
         }
     }
     __syncthreads();
@@ -342,19 +372,31 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     }
 }
 
-template <int N, int D, int TRW, int ALAY>
-static int odd_fwd_last_A(fh_ga* op, double* p, const double* r, int pupdate) {
+template <int N, int D, int TRW, int ALAY, int V>
+static int odd_fwd_last_AV(fh_ga* op, double* p, const double* r, int pupdate) {
     constexpr int NP = D * TRW / 2;
     const size_t smem = (size_t)2 * NP * (N + 1) * sizeof(double);
     const unsigned nblk = (unsigned)fh_ceil_div(op->nrows, TRW);
     const fh_plan* pl = op->plan;
     int rc;
-    if ((rc = odd_smem_attr(k_fwd_last_odd<N, D, TRW, ALAY>, smem))) return rc;
-    k_fwd_last_odd<N, D, TRW, ALAY><<<nblk, NP * FastCfg<N>::TPL, smem, fh_stream()>>>(
+    if ((rc = odd_smem_attr(k_fwd_last_odd<N, D, TRW, ALAY, V>, smem))) return rc;
+    k_fwd_last_odd<N, D, TRW, ALAY, V><<<nblk, NP * FastCfg<N>::TPL, smem, fh_stream()>>>(
         op->A, op->phase, op->lut, op->lutc, op->nphase, p, r, op->scal, pupdate, op->spec, pl->ax[pl->dim - 1].tw,
         op->nrows, pl->nh, op->pitch, op->xacc);
     FH_LAUNCH_CHECK();
     return FH_OK;
+}
+// voxels per thread and step of phase 0 (loads in flight).  Measured at 255^3 scalar, symmetric coefficients (S1 plain):
+// V = 2 0.412 ms, V = 3 0.484, V = 4 0.491 (the register cap of two CTAs per SM makes the wider steps spill); D = 6: one
+template <int N, int D, int TRW, int ALAY>
+static int odd_fwd_last_A(fh_ga* op, double* p, const double* r, int pupdate) {
+    if (D == 3) {
+        static const int v = odd_env("FH_ODD_V", 2);
+        if (v == 4) return odd_fwd_last_AV<N, D, TRW, ALAY, 4>(op, p, r, pupdate);
+        if (v == 3) return odd_fwd_last_AV<N, D, TRW, ALAY, 3>(op, p, r, pupdate);
+        return odd_fwd_last_AV<N, D, TRW, ALAY, 2>(op, p, r, pupdate);
+    }
+    return odd_fwd_last_AV<N, D, TRW, ALAY, 1>(op, p, r, pupdate);
 }
 template <int N, int D, int TRW>
 static int odd_fwd_last_D(fh_ga* op, double* p, const double* r, int pupdate) {
@@ -376,7 +418,7 @@ int fh_odd_fwd_last(fh_ga* op, double* p, const double* r, int pupdate) {
 
 // ------------------------------------------------------------------ S5: C2R along the last axis, y = scale * result, <p, y>
 template <int N, int D, int TRW>
-__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
+__global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL, 2)
     k_inv_last_odd(const cplx* __restrict__ spec, double* __restrict__ y, const double* __restrict__ pdot,
                    double* __restrict__ part, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
                    double scale) {
@@ -390,7 +432,7 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     const int64_t row0 = (int64_t)blockIdx.x * TRW;
     // phase 0: Z = X_a + i X_b on the full circle (Hermitian completion), natural order; U independent 16-byte loads
     // per thread are issued before any is consumed
-    constexpr int U = 4;
+    constexpr int U = 8;
     for (int it0 = threadIdx.x; it0 < NP * nh; it0 += U * NT) {
         cplx a[U], b[U];
         int prs[U], ks[U];
@@ -451,27 +493,37 @@ __global__ void __launch_bounds__((D * TRW / 2) * FastCfg<N>::TPL)
     // inverse of pass 1: registers hold z[j + rr*R2]; re -> line 2*pr, im -> line 2*pr+1
     double acc = 0.0;
     if (j < R2) {
-        cplx v[R1];
-#pragma unroll
-        for (int q = 0; q < R1; ++q) v[q] = make_double2(lre[j * R1 + q], lim[j * R1 + q]);
-        Bfly<R1, true>::run(v);
         const int La = 2 * pr, Lb = 2 * pr + 1;
         const int ca = La / TRW, ra = La - ca * TRW, cb = Lb / TRW, rb = Lb - cb * TRW;
         const bool la = row0 + ra < nrows, lb = row0 + rb < nrows;
         const size_t oa = ((size_t)ca * nrows + row0 + ra) * N, ob = ((size_t)cb * nrows + row0 + rb) * N;
+        // the operand of <p, y> is fetched before the butterfly: its latency hides behind the arithmetic (ncu, round 2:
+        // loaded inside the store loop, every one of the 2*R1 loads was waited for in turn)
+        double pa[R1], pb[R1];
+        if (pdot) {
+#pragma unroll
+            for (int rr = 0; rr < R1; ++rr) {
+                pa[rr] = la ? pdot[oa + j + rr * R2] : 0.0;
+                pb[rr] = lb ? pdot[ob + j + rr * R2] : 0.0;
+            }
+        }
+        cplx v[R1];
+#pragma unroll
+        for (int q = 0; q < R1; ++q) v[q] = make_double2(lre[j * R1 + q], lim[j * R1 + q]);
+        Bfly<R1, true>::run(v);
+        double acc2 = 0.0;
 #pragma unroll
         for (int rr = 0; rr < R1; ++rr) {
             const int i2 = j + rr * R2;
             const double ya = v[rr].x * scale, yb = v[rr].y * scale;
-            if (la) {
-                y[oa + i2] = ya;
-                if (pdot) acc += pdot[oa + i2] * ya;
-            }
-            if (lb) {
-                y[ob + i2] = yb;
-                if (pdot) acc += pdot[ob + i2] * yb;
+            if (la) y[oa + i2] = ya;
+            if (lb) y[ob + i2] = yb;
+            if (pdot) {
+                acc += pa[rr] * ya;
+                acc2 += pb[rr] * yb;
             }
         }
+        acc += acc2;
     }
     if (pdot) {
         acc = block_sum(acc, red);

@@ -1,1 +1,1 @@
-from .objects import Matrix, VecTri, Scalar, DFT, LinOper  # noqa: F401
+from .objects import Matrix, VecTri, Scalar, DFT, LinOper, MultiVector, MultiOper, ScipyOper  # noqa: F401

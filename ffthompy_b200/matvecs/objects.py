@@ -530,6 +530,145 @@ class LinOper():
         return LinOper(name='(%s)^T' % self.name, mat=mat)
 
 
+class MultiVector():
+    """Block vector of mixed formulations: an ordered list of sub-vectors (VecTri) that adds, negates, scales and
+    contracts block by block (matvecs/objects.py:938-1053).  The blocks keep their device storage; only `vec()`
+    assembles a host array."""
+
+    def __init__(self, name='MultiVector', val=None):
+        self.name = name
+        self.val = list(val)
+        self.dim = len(self.val)
+        self._iter = np.arange(self.dim)
+        self.ltype = [type(b).__name__ for b in self.val]
+        self.lshape, self.ldtype = [], []
+        self.lsize = np.zeros(self.dim, dtype=np.int64)
+        for m, b in enumerate(self.val):
+            if isinstance(b, VecTri):
+                self.lshape.append(b.valshape)
+                self.ldtype.append(getattr(b, 'dtype', np.float64))
+                self.lsize[m] = b.size
+        self.size = int(np.sum(self.lsize))
+
+    def _map(self, fun, name=None):
+        return MultiVector(name=self.name if name is None else name, val=[fun(b) for b in self.val])
+
+    def __mul__(self, x):
+        if isinstance(x, MultiVector):          # block-wise scalar product, summed
+            return sum((a*b for a, b in zip(self.val[1:], x.val[1:])), self.val[0]*x.val[0])
+        if isinstance(x, Scalar):
+            return self._map(lambda b: x.val*b)
+        if np.size(x) == 1:
+            c = float(np.asarray(x).ravel()[0])
+            return self._map(lambda b: c*b)
+        raise NotImplementedError()
+
+    __rmul__ = __mul__
+    __call__ = __mul__
+
+    def __add__(self, x):
+        return MultiVector(val=[a+b for a, b in zip(self.val, x.val)])
+
+    def __neg__(self):
+        return self._map(lambda b: -b)
+
+    def __sub__(self, x):
+        return self+(-x)
+
+    def __getitem__(self, m):
+        return self.val[m]
+
+    def vec(self):
+        return np.vstack([np.asarray(b.vec()) for b in self.val])
+
+    def __eq__(self, x):
+        same = [type(a).__name__ == type(b).__name__ for a, b in zip(self.val, x.val)]
+        vals = [(a == b) if t else False for a, b, t in zip(self.val, x.val, same)]
+        return 'subvector types : %s; subvector equality : %s' % (str(same), str(vals))
+
+    __hash__ = object.__hash__
+
+    def __repr__(self):
+        s = 'Class : %s\n    name : %s\n' % (self.__class__.__name__, self.name)
+        s += '    dim = %d ; size = %d\n' % (self.dim, self.size)
+        s += '    blocks : [ %s ]\n' % ' , '.join('%s(%s)' % (getattr(b, 'name', '?'), t)
+                                                  for b, t in zip(self.val, self.ltype))
+        return s+''.join(str(b) for b in self.val)
+
+
+class MultiOper():
+    """Block operator acting on a MultiVector: row m of the result is sum_n val[m][n]*x[n]
+    (matvecs/objects.py:1056-1101)."""
+
+    def __init__(self, name='MultiOper', val=None):
+        self.name = name
+        self.val = [list(row) for row in val]
+        self.no_row, self.no_col = len(self.val), len(self.val[0])
+        self.shape = (self.no_row, self.no_col)
+
+    def __call__(self, x):
+        if not isinstance(x, MultiVector):
+            raise NotImplementedError('MultiOper acts on a MultiVector')
+        rows = []
+        for row in self.val:
+            acc = row[0]*x[0]
+            for op, xb in zip(row[1:], x.val[1:]):
+                acc = acc+op*xb
+            rows.append(acc)
+        return MultiVector(val=rows)
+
+    __mul__ = __call__
+
+    def transpose(self):
+        return MultiOper(name='(%s)^T' % self.name,
+                         val=[[self.val[n][m].transpose() for n in range(self.no_row)] for m in range(self.no_col)])
+
+    def __repr__(self):
+        s = 'Class : %s\n    name : %s\n    expression :\n' % (self.__class__.__name__, self.name)
+        for row in self.val:
+            s += '        [ %s ]\n' % ' , '.join(op.name for op in row)
+        return s
+
+
+class ScipyOper():
+    """matvec / rmatvec of a (block) operator over flat host vectors, the shape scipy.sparse.linalg expects
+    (matvecs/objects.py:1104-1165); `X` fixes the block structure of the operand."""
+
+    def __init__(self, name='ScipyLinOper', A=None, X=None, AT=None, dtype=None):
+        self.name = name
+        self.A = A
+        self.dtype = np.float64 if dtype is None else dtype
+        if AT is not None:
+            self.AT = AT
+        Y = A(X)
+        self.shape = (Y.size, X.size)
+        self.X, self.Y = X, Y
+
+    def revec(self, x):
+        x = np.asarray(x).ravel()
+        if isinstance(self.X, VecTri):
+            return VecTri(val=np.reshape(x, self.X._vshape()))
+        blocks, end = [], 0
+        for m in self.X._iter:
+            beg, end = end, end+int(self.X.lsize[m])
+            if self.X.ltype[m] != 'VecTri':
+                raise NotImplementedError('ScipyOper: block type %s' % self.X.ltype[m])
+            blocks.append(VecTri(val=np.reshape(x[beg:end], self.X.lshape[m])))
+        return MultiVector(val=blocks)
+
+    revecD = revec
+
+    def matvec(self, x):
+        return self.A(self.revec(x)).vec()
+
+    def rmatvec(self, x):
+        return self.AT(self.revecD(x)).vec()
+
+    def __repr__(self):
+        return 'Class : %s\n    name : %s\n    shape = %s\n    A : %s\n' % (self.__class__.__name__, self.name,
+                                                                             str(self.shape), self.A.name)
+
+
 def enlargeF(xN, M):
     """Spectral interpolation of grid values to the grid M (matvecs/objects.py:1158-1178)."""
     N = tuple(int(n) for n in np.shape(xN))

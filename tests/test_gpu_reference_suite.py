@@ -245,3 +245,47 @@ def test_legacy_matvec():
         xo, io = O.cg(Afun, Afun(-Ev), np.zeros_like(Ev), 1e-8, 100, N)
         assert info['kit'] == io['kit']
         assert np.abs(X.val-xo).max() < 1e-10
+
+
+def test_block_vectors_and_operators():
+    """MultiVector / MultiOper / ScipyOper (matvecs/objects.py:938-1165): block algebra against NumPy on the host values"""
+    from ffthompy_b200.matvecs import VecTri, Matrix, MultiVector, MultiOper, ScipyOper, Scalar
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        N = np.array([5, 4])
+        rng = np.random.default_rng(7)
+        u = [VecTri(name='u%d' % i, val=rng.standard_normal((2, 5, 4))) for i in range(2)]
+        v = [VecTri(name='v%d' % i, val=rng.standard_normal((2, 5, 4))) for i in range(2)]
+        U, V = MultiVector(val=u), MultiVector(val=v)
+        assert U.dim == 2 and U.size == 2*2*5*4 and U.ltype == ['VecTri', 'VecTri']
+        # scalar product = sum of the block scalar products (each 1/prod(N)-weighted, as VecTri*VecTri)
+        ref = sum(np.sum(a.val*b.val) for a, b in zip(u, v))/np.prod(N)
+        assert abs(U*V-ref) < 1e-13
+        W = U+V
+        assert all(np.abs(W[m].val-(u[m].val+v[m].val)).max() < 1e-15 for m in range(2))
+        W = U-V
+        assert all(np.abs(W[m].val-(u[m].val-v[m].val)).max() < 1e-15 for m in range(2))
+        W = Scalar(val=2.5)*U
+        assert all(np.abs(W[m].val-2.5*u[m].val).max() < 1e-15 for m in range(2))
+        assert np.abs(np.asarray(U.vec()).ravel()-np.hstack([a.val.ravel() for a in u])).max() == 0
+        # block operator of pointwise matrices
+        Mv = [[rng.standard_normal((2, 2, 5, 4)) for _ in range(2)] for _ in range(2)]
+        Op = MultiOper(val=[[Matrix(name='M%d%d' % (m, n), val=Mv[m][n]) for n in range(2)] for m in range(2)])
+        Y = Op(U)
+        for m in range(2):
+            ref = sum(np.einsum('ij...,j...->i...', Mv[m][n], u[n].val) for n in range(2))
+            assert np.abs(Y[m].val-ref).max() < 1e-13
+        Yt = Op.transpose()(U)
+        for m in range(2):
+            ref = sum(np.einsum('ji...,j...->i...', Mv[n][m], u[n].val) for n in range(2))
+            assert np.abs(Yt[m].val-ref).max() < 1e-13
+        # flat-vector bridge
+        S = ScipyOper(A=Op, X=U, AT=Op.transpose())
+        assert S.shape == (U.size, U.size)
+        x = rng.standard_normal(U.size)
+        y = np.asarray(S.matvec(x)).ravel()
+        yref = np.asarray(Op(S.revec(x)).vec()).ravel()
+        assert np.abs(y-yref).max() < 1e-14
+        # <A x, z> == <x, A^T z>
+        z = rng.standard_normal(U.size)
+        assert abs(np.dot(y, z)-np.dot(x, np.asarray(S.rmatvec(z)).ravel())) < 1e-11
