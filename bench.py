@@ -755,7 +755,7 @@ def run_slab(args):
         E2 = dev.zeros(shape)
         E2[0] = -1.
         X, info = op2.cg(op2.apply(E2), dev.zeros(shape), tol=1e-6, maxiter=1000)
-        x_host = X.cpu()
+        x_host = dev.download(X)                  # fresh pageable host array, as Tensor.val hands out (csrc/fh_host.cu)
         torch.cuda.synchronize()
         tt = torch.tensor([time.perf_counter()-t0], dtype=torch.float64, device=dev.device())
         # A_H[0,0] = <A e, e>, e = X + e_0 (postprocess.py:53-70), for the 1 <-> N GPU agreement check
@@ -768,7 +768,7 @@ def run_slab(args):
         t_e2e = float(tt.item())
         kit = info['kit']
         e2e = {'value': D*nvox*kit/t_e2e, 'unit': 'voxel-DOF/s',
-               'h2d_bytes_per_step': int(world*A_host.numel()*8/kit), 'd2h_bytes_per_step': int(world*x_host.numel()*8/kit),
+               'h2d_bytes_per_step': int(world*A_host.numel()*8/kit), 'd2h_bytes_per_step': int(world*x_host.size*8/kit),
                'cg_iterations': kit, 'seconds': t_e2e, 'A_H00': ah00,
                'what': 'SlabGA(A_slab).cg(tol 1e-6) on every rank: pinned-host coefficient slab uploaded, operator '
                        'set-up (symmetric-memory rendezvous included), solve, solution slab downloaded; wall clock, '

@@ -37,7 +37,7 @@ def build(force=False, verbose=False):
         objs.append(o)
         # fh_reg3.cuh (kernel bodies) is included by fh_reg3.cu only; the other units see fh_reg3.h
         # kernel-body headers that only some units include (keeps the 7-minute fh_fused.cu out of their edit cycle)
-        private = {'fh_reg3.cuh': ('fh_reg3.cu',), 'fh_mid2.cuh': ('fh_mid2.cu', 'fh_mid512.cu'),
+        private = {'fh_reg3.cuh': ('fh_reg3.cu',), 'fh_mid2.cuh': ('fh_mid2.cu', 'fh_mid512.cu'), 'fh_mid3.cuh': ('fh_mid2.cu',),
                    'fh_mid512.h': ('fh_reg3.cu', 'fh_mid512.cu'), 'fh_odd.h': ('fh_fused.cu', 'fh_odd.cu')}
         deps = [h for h in hdrs if os.path.basename(h) not in private or src in private[os.path.basename(h)]]
         if force or _stale(o, [s] + deps):

@@ -1,6 +1,7 @@
 // fh_mid2.cu — launchers of the 8-column axis-0 + G^ kernels (fh_mid2.cuh).  Internal C++ interface (fh_mid2.h)
 // used by the fused operator in fh_fused.cu; nothing here is part of the C ABI.
 #include "fh_mid2.cuh"
+#include "fh_mid3.cuh"
 #include "fh_mid2.h"
 #include <stdlib.h>
 
@@ -10,8 +11,24 @@ static int mid2_env(const char* name, int dflt) {
 }
 bool fh_mid2_can(int n) { return n == 128 || n == 256; }
 bool fh_mid2_len(int n) {
-    static const int on = mid2_env("FH_MID2", 0);  // opt-in: measured slower than k_mid_green_pipe
+    // 0: k_mid_green_pipe; 1: the 8-column kernel of fh_mid2.cuh (measured slower);
+    // 2: the row-group-per-warp kernel of fh_mid3.cuh (N0 = 256)
+    static const int on = mid2_env("FH_MID2", 0);
+    if (on == 2) return n == 256;
     return on && (n == 128 || n == 256);  // (64 keeps the round-1 kernel: 64 threads per CTA would leave the SM idle)
+}
+
+template <int KIND>
+static int mid3_launch(cplx* data, const cplx* tw, const GreenDesc& g, const Mid3Map& m, int nh) {
+    using Cfg = Mid3Cfg<KIND>;
+    if (Cfg::SMEM > (size_t)fh_max_smem_optin())
+        return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: %zu bytes of shared memory", Cfg::SMEM);
+    FH_CUDA(cudaFuncSetAttribute(k_mid3<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    int grid = fh_num_sms();
+    if (grid > m.ntiles) grid = m.ntiles;
+    k_mid3<KIND><<<grid, Cfg::NT, Cfg::SMEM, fh_stream()>>>(data, tw, g, m, nh);
+    FH_LAUNCH_CHECK();
+    return FH_OK;
 }
 
 template <int N, int KIND, int MINB, int PREF>
@@ -52,6 +69,18 @@ int fh_mid2_green(int N, int kind, cplx* data, const cplx* tw, const GreenDesc& 
     if (spitch % 8 || col0 % 8 || ncols % 8 || ncols <= 0)
         return fh_set_error(FH_ERR_UNSUPPORTED, "axis-0 pass: 8-column tiles need 128-byte aligned rows (pitch %d, columns %d+%d)",
                             spitch, col0, ncols);
+    static const int which = mid2_env("FH_MID2", 0);
+    if (which == 2 && N == 256 && !rowoff && !dout && kcol0 == 0) {
+        Mid3Map m3;
+        m3.rstride = rstride;
+        m3.cstride = cstride;
+        m3.spitch = spitch;
+        m3.tpr = ncols / 4;
+        m3.ntiles = nrow * m3.tpr;
+        m3.col0 = col0;
+        return (kind == FH_GREEN_ELASTIC) ? mid3_launch<FH_GREEN_ELASTIC>(data, tw, g, m3, nh)
+                                          : mid3_launch<FH_GREEN_SCALAR>(data, tw, g, m3, nh);
+    }
     Mid2Map m;
     m.rowoff = rowoff;
     m.rstride = rstride;

@@ -26,7 +26,7 @@ bool fh_reg3_mid_len(int n) {
 
 template <int N, int D, int TRW, int ALAY>
 static int fwd_last_A(const Reg3LastArgs& a) {
-    constexpr int NP = D * TRW / 2, NPAD = N + N / 8;
+    constexpr int NP = D * TRW / 2, NPAD = LinePad<N>::NPAD;
     const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
     int rc;
     if ((rc = reg3_smem_attr(k_fwd_last_reg3<N, D, TRW, ALAY>, smem))) return rc;
@@ -56,7 +56,7 @@ int fh_reg3_fwd_last(int N, int D, int trw, const Reg3LastArgs& a) {
 
 template <int N, int D, int TRW>
 static int inv_last_D(const Reg3InvArgs& a) {
-    constexpr int NP = D * TRW / 2, NPAD = N + N / 8;
+    constexpr int NP = D * TRW / 2, NPAD = LinePad<N>::NPAD;
     const size_t smem = (size_t)2 * NP * NPAD * sizeof(double);
     int rc;
     if ((rc = reg3_smem_attr(k_inv_last_reg3<N, D, TRW>, smem))) return rc;

@@ -31,8 +31,29 @@ __host__ __device__ __forceinline__ int reg3_freq_of_pos(int pos) {
     return q + R1 * (q2 + R2 * k);
 }
 
+// Padding of one SoA line (8-byte elements, sixteen 8-byte banks per 128-byte wavefront, conflicts counted per half
+// warp).  ncu, round 2 (512^3, profiles/r02b_ncu_512_last_axis.md): with one padding element per 8 (pidx8) S1 and S5 ran at
+// 96 % / 92 % of the L1/shared-memory throughput with every second wavefront a bank conflict - the S1 stores of phase 0,
+// both sides of pass 1 and above all the digit-reversed gathers / scatters of the R2C / C2R separation (8 wavefronts
+// instead of 2).  For 512 = 8 x 8 x 8 an exhaustive search over paddings p + a p/8 + b p/16 + c p/32 + d p/64 + e p/128 and
+// the two lane orders of the pass-2 butterflies gives  p + p/16 + 2 (p/32) + 2 (p/64)  with q fastest in pass 2: every
+// access of the three passes and of phase 0 is conflict free, the separation costs 4 instead of 8 (24.5 wavefronts per
+// element and direction instead of 40; 20 is the floor).
+template <int N>
+struct LinePad {
+    static constexpr int NPAD = N + N / 8;
+    static constexpr bool SWAP2 = false;
+    static __host__ __device__ __forceinline__ int idx(int p) { return p + (p >> 3); }
+};
+template <>
+struct LinePad<512> {
+    static constexpr int NPAD = 588;  // idx(511) = 586
+    static constexpr bool SWAP2 = true;
+    static __host__ __device__ __forceinline__ int idx(int p) { return p + (p >> 4) + 2 * (p >> 5) + 2 * (p >> 6); }
+};
+
 // ------------------------------------------------------------------ one line in SoA shared memory (last-axis kernels)
-// lre / lim: the line's real / imaginary planes, element `pos` at [pidx8(pos)].  u = butterfly index of this
+// lre / lim: the line's real / imaginary planes, element `pos` at [LinePad<N>::idx(pos)].  u = butterfly index of this
 // thread inside the line (0 .. TPL-1).  All threads of the CTA must call (block-wide barriers inside).
 template <int N>
 __device__ __forceinline__ void reg3_line_fwd(double* __restrict__ lre, double* __restrict__ lim, int u,
@@ -42,30 +63,30 @@ __device__ __forceinline__ void reg3_line_fwd(double* __restrict__ lre, double* 
     if (u < Reg3Cfg<N>::B1) {
         cplx v[R1];
 #pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = make_double2(lre[pidx8(u + r * M)], lim[pidx8(u + r * M)]);
+        for (int r = 0; r < R1; ++r) v[r] = make_double2(lre[LinePad<N>::idx(u + r * M)], lim[LinePad<N>::idx(u + r * M)]);
         Bfly<R1, false>::run(v);
 #pragma unroll
         for (int q = 1; q < R1; ++q) v[q] = cmul(v[q], ldtw(tw, q * u, false));
 #pragma unroll
         for (int q = 0; q < R1; ++q) {
-            lre[pidx8(q * M + u)] = v[q].x;
-            lim[pidx8(q * M + u)] = v[q].y;
+            lre[LinePad<N>::idx(q * M + u)] = v[q].x;
+            lim[LinePad<N>::idx(q * M + u)] = v[q].y;
         }
     }
     __syncthreads();
     if (u < Reg3Cfg<N>::B2) {
-        const int q = u / R3, jp = u - q * R3;
+        const int q = LinePad<N>::SWAP2 ? u % R1 : u / R3, jp = LinePad<N>::SWAP2 ? u / R1 : u - (u / R3) * R3;
         const int b = q * M + jp;
         cplx v[R2];
 #pragma unroll
-        for (int r = 0; r < R2; ++r) v[r] = make_double2(lre[pidx8(b + r * R3)], lim[pidx8(b + r * R3)]);
+        for (int r = 0; r < R2; ++r) v[r] = make_double2(lre[LinePad<N>::idx(b + r * R3)], lim[LinePad<N>::idx(b + r * R3)]);
         Bfly<R2, false>::run(v);
 #pragma unroll
         for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, false));
 #pragma unroll
         for (int q2 = 0; q2 < R2; ++q2) {
-            lre[pidx8(b + q2 * R3)] = v[q2].x;
-            lim[pidx8(b + q2 * R3)] = v[q2].y;
+            lre[LinePad<N>::idx(b + q2 * R3)] = v[q2].x;
+            lim[LinePad<N>::idx(b + q2 * R3)] = v[q2].y;
         }
     }
     __syncthreads();
@@ -74,12 +95,12 @@ __device__ __forceinline__ void reg3_line_fwd(double* __restrict__ lre, double* 
         const int b = q * M + q2 * R3;
         cplx v[R3];
 #pragma unroll
-        for (int jp = 0; jp < R3; ++jp) v[jp] = make_double2(lre[pidx8(b + jp)], lim[pidx8(b + jp)]);
+        for (int jp = 0; jp < R3; ++jp) v[jp] = make_double2(lre[LinePad<N>::idx(b + jp)], lim[LinePad<N>::idx(b + jp)]);
         Bfly<R3, false>::run(v);
 #pragma unroll
         for (int k = 0; k < R3; ++k) {
-            lre[pidx8(b + k)] = v[k].x;
-            lim[pidx8(b + k)] = v[k].y;
+            lre[LinePad<N>::idx(b + k)] = v[k].x;
+            lim[LinePad<N>::idx(b + k)] = v[k].y;
         }
     }
     __syncthreads();
@@ -96,34 +117,34 @@ __device__ __forceinline__ void reg3_line_inv(double* __restrict__ lre, double* 
         const int b = q * M + q2 * R3;
         cplx v[R3];
 #pragma unroll
-        for (int k = 0; k < R3; ++k) v[k] = make_double2(lre[pidx8(b + k)], lim[pidx8(b + k)]);
+        for (int k = 0; k < R3; ++k) v[k] = make_double2(lre[LinePad<N>::idx(b + k)], lim[LinePad<N>::idx(b + k)]);
         Bfly<R3, true>::run(v);
 #pragma unroll
         for (int jp = 0; jp < R3; ++jp) {
-            lre[pidx8(b + jp)] = v[jp].x;
-            lim[pidx8(b + jp)] = v[jp].y;
+            lre[LinePad<N>::idx(b + jp)] = v[jp].x;
+            lim[LinePad<N>::idx(b + jp)] = v[jp].y;
         }
     }
     __syncthreads();
     if (u < Reg3Cfg<N>::B2) {
-        const int q = u / R3, jp = u - q * R3;
+        const int q = LinePad<N>::SWAP2 ? u % R1 : u / R3, jp = LinePad<N>::SWAP2 ? u / R1 : u - (u / R3) * R3;
         const int b = q * M + jp;
         cplx v[R2];
 #pragma unroll
-        for (int q2 = 0; q2 < R2; ++q2) v[q2] = make_double2(lre[pidx8(b + q2 * R3)], lim[pidx8(b + q2 * R3)]);
+        for (int q2 = 0; q2 < R2; ++q2) v[q2] = make_double2(lre[LinePad<N>::idx(b + q2 * R3)], lim[LinePad<N>::idx(b + q2 * R3)]);
 #pragma unroll
         for (int q2 = 1; q2 < R2; ++q2) v[q2] = cmul(v[q2], ldtw(tw, R1 * jp * q2, true));
         Bfly<R2, true>::run(v);
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
-            lre[pidx8(b + r * R3)] = v[r].x;
-            lim[pidx8(b + r * R3)] = v[r].y;
+            lre[LinePad<N>::idx(b + r * R3)] = v[r].x;
+            lim[LinePad<N>::idx(b + r * R3)] = v[r].y;
         }
     }
     __syncthreads();
     if (u < Reg3Cfg<N>::B1) {
 #pragma unroll
-        for (int q = 0; q < R1; ++q) out[q] = make_double2(lre[pidx8(q * M + u)], lim[pidx8(q * M + u)]);
+        for (int q = 0; q < R1; ++q) out[q] = make_double2(lre[LinePad<N>::idx(q * M + u)], lim[LinePad<N>::idx(q * M + u)]);
 #pragma unroll
         for (int q = 1; q < R1; ++q) out[q] = cmul(out[q], ldtw(tw, q * u, true));
         Bfly<R1, true>::run(out);
@@ -133,15 +154,17 @@ __device__ __forceinline__ void reg3_line_inv(double* __restrict__ lre, double* 
 // ------------------------------------------------------------------ S1: sigma = A p (+ CG updates), R2C last axis
 // Same contract as k_fwd_last_fast (fh_fast.cuh): real fields [D][rows][N], TRW rows of all D components
 // per CTA, two real lines per complex transform; blockDim = NP * TPL.
+// (three CTAs per SM: the CG form lives on the loads in flight; without the cap the 512 padding arithmetic takes the
+// kernel to 72 registers = two CTAs and S1 in its CG form loses 5 %)
 template <int N, int D, int TRW, int ALAY>
-__global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
+__global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL, 3)
     k_fwd_last_reg3(const double* __restrict__ A, const unsigned char* __restrict__ phase,
                     const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
                     const double* __restrict__ r, const double* __restrict__ scal, int pupdate,
                     cplx* __restrict__ spec, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
                     double* __restrict__ xacc) {
     constexpr int TPL = Reg3Cfg<N>::TPL;
-    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 8;
+    constexpr int NL = D * TRW, NP = NL / 2, NPAD = LinePad<N>::NPAD;
     constexpr int NT = NP * TPL;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     double* smd = reinterpret_cast<double*>(fh_smem_raw);
@@ -159,8 +182,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
     s1_sigma_phase<N, D, TRW, ALAY, NT>(A, phase, slut, lutc, p, r, beta, pupdate, row0, n,
                                         [&](int L, int i2, double s0, double s1) {
                                             double* dst = ((L & 1) ? zim : zre) + (L >> 1) * NPAD;
-                                            dst[pidx8(i2)] = s0;
-                                            dst[pidx8(i2 + 1)] = s1;
+                                            dst[LinePad<N>::idx(i2)] = s0;
+                                            dst[LinePad<N>::idx(i2 + 1)] = s1;
                                         },
                                         xacc, alpha);
     __syncthreads();
@@ -174,8 +197,8 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
         if (k < nh) {
             const double* qre = zre + (L >> 1) * NPAD;
             const double* qim = zim + (L >> 1) * NPAD;
-            const int pk = pidx8(reg3_pos_of_freq<N>(k));
-            const int pm = pidx8(reg3_pos_of_freq<N>((k == 0) ? 0 : N - k));
+            const int pk = LinePad<N>::idx(reg3_pos_of_freq<N>(k));
+            const int pm = LinePad<N>::idx(reg3_pos_of_freq<N>((k == 0) ? 0 : N - k));
             const double ax_ = qre[pk], ay_ = qim[pk];
             const double bx_ = qre[pm], by_ = qim[pm];
             X = (L & 1) ? make_double2(0.5 * (ay_ + by_), -0.5 * (ax_ - bx_))
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
                     double* __restrict__ part, const cplx* __restrict__ tw, int64_t nrows, int nh, int pitch,
                     double scale) {
     constexpr int R1 = Reg3Cfg<N>::R1, TPL = Reg3Cfg<N>::TPL, M = N / R1;
-    constexpr int NL = D * TRW, NP = NL / 2, NPAD = N + N / 8;
+    constexpr int NL = D * TRW, NP = NL / 2, NPAD = LinePad<N>::NPAD;
     constexpr int NT = NP * TPL;
     extern __shared__ __align__(16) unsigned char fh_smem_raw[];
     double* smd = reinterpret_cast<double*>(fh_smem_raw);
@@ -231,11 +254,11 @@ __global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL)
             }
             double* qre = zre + prs[uu] * NPAD;
             double* qim = zim + prs[uu] * NPAD;
-            const int pk = pidx8(reg3_pos_of_freq<N>(k));
+            const int pk = LinePad<N>::idx(reg3_pos_of_freq<N>(k));
             qre[pk] = av.x - bv.y;
             qim[pk] = av.y + bv.x;
             if (k > 0 && 2 * k != N) {
-                const int pm = pidx8(reg3_pos_of_freq<N>(N - k));
+                const int pm = LinePad<N>::idx(reg3_pos_of_freq<N>(N - k));
                 qre[pm] = av.x + bv.y;
                 qim[pm] = -av.y + bv.x;
             }

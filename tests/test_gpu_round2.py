@@ -115,16 +115,18 @@ def test_one_pass_assembly_equals_pairwise(N, D):
     assert np.abs(AH-ref).max() <= 1e-13*np.abs(ref).max()
 
 
-def test_mid2_kernel_is_opt_in_and_correct():
-    """FH_MID2=1 selects the 8-column axis-0 + Green kernel (csrc/fh_mid2.cuh); measured slower than the default
-    (DESIGN.md section 4), kept behind the switch with its parity check"""
+@pytest.mark.parametrize('which', ['1', '2'])
+def test_mid2_kernel_is_opt_in_and_correct(which):
+    """FH_MID2=1 selects the 8-column axis-0 + Green kernel (csrc/fh_mid2.cuh), FH_MID2=2 the row-group-per-warp kernel
+    (csrc/fh_mid3.cuh, N0 = 256); kept behind the switch with their parity check (measurements: DESIGN.md section 4)"""
     code = r'''
 import numpy as np
 import ffthom_oracle as O, harness
 from ffthompy_b200 import device
 from ffthompy_b200.tensors import Tensor
 device.init(0)
-for N, phys in [((256, 8, 16), 'elasticity'), ((128, 16, 16), 'elasticity'), ((256, 16, 8), 'scalar')]:
+for N, phys in [((256, 8, 16), 'elasticity'), ((128, 16, 16), 'elasticity'), ((256, 16, 8), 'scalar'),
+                ((256, 5, 20), 'elasticity')]:
     d = 3
     D = 6 if phys == 'elasticity' else 3
     G = harness.green_for(phys, 'GaNi', N, np.ones(3), 'primal')[0]
@@ -143,6 +145,6 @@ print('MID2 OK')
 '''
     here = os.path.dirname(os.path.abspath(harness.__file__))
     root = os.path.dirname(here)
-    env = dict(os.environ, FH_MID2='1', PYTHONPATH=os.pathsep.join([root, os.path.join(root, 'oracle'), here]))
+    env = dict(os.environ, FH_MID2=which, PYTHONPATH=os.pathsep.join([root, os.path.join(root, 'oracle'), here]))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and 'MID2 OK' in r.stdout, r.stdout[-1500:]+r.stderr[-1500:]
