@@ -541,6 +541,7 @@ def run_ours(args):
 
     extras = {}
     if not args.no_extras and world == 1:
+        extras['config1_2d_31'] = bench_config1(torch, dev, K, W)
         extras['config2_255'] = bench_config2(torch, dev, L, lib, K, W, peak)
         torch.cuda.empty_cache()
         extras['strong_base'] = bench_512_single(torch, dev, K, W, peak)
@@ -567,9 +568,35 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def bench_config1(torch, dev, K, W):
+    """BASELINE config 1 in shape (tutorials/02_homogenisation.py: 2-D scalar, square inclusion, N = 31 x 31, GaNi):
+    microseconds per CG iteration of the device loop.  At this size the iteration is launch-latency bound (8 kernels
+    and one 8-byte read-back), not bandwidth bound; the number is reported for completeness, not against a roofline."""
+    from ffthompy_b200.tensors import Tensor, DFT, Operator
+    import ffthompy_b200.projections as proj
+    n, D = 31, 2
+    N = np.array([n, n])
+    xs = (np.arange(n)-n//2)/n
+    incl = (np.abs(xs)[:, None] < 0.3) & (np.abs(xs)[None, :] < 0.3)
+    Aval = np.einsum('ij,...->ij...', np.eye(2), 1.+10.*incl)
+    A = Tensor(name='A', val=Aval, order=2, N=N, multype=21)
+    _, G, _ = proj.scalar(N, np.ones(2), NyqNul=True, tensor=True)
+    GN = Operator(name='G1', mat=[[DFT(name='FiN', inverse=True, N=N), G, DFT(name='FN', inverse=False, N=N)]])
+    Afun = Operator(name='FiGFA', mat=[[GN, A]])
+    EN = Tensor(name='EN', N=N, shape=(D,), Fourier=False)
+    EN.set_mean(np.eye(D)[0])
+    B = Afun(-EN)
+    f = Afun.fused()
+    ms, launches, x, vecs = timed_cg(f, B._dev(), D, (n, n), max(K, 50), W)
+    del x, vecs
+    return {'workload': '2-D scalar (D=2), square inclusion, GaNi 31 x 31 (tutorial 02 shape)', 'grid': [n, n],
+            'us_per_iteration': ms*1e3, 'cg_iterations_per_s': 1e3/ms, 'launches_per_iteration': launches/max(K, 50),
+            'note': 'launch-latency bound: kernels + one 8-byte read-back per iteration'}
+
+
 def bench_config2(torch, dev, L, lib, K, W, peak):
     """BASELINE config 2 in shape: 3-D scalar (D = 3), N = 128^3 solved on the exact-integration grid Nbar = 255^3
-    (= 3*5*17: the run-time-length kernels), Ga projection with the reference's prod(Nbar)/prod(N) scale.  The
+    (= 15*17: the compile-time odd-length kernels of csrc/fh_odd.cu), Ga projection with the reference's prod(Nbar)/prod(N) scale.  The
     coefficient field is a synthetic non-piecewise-constant isotropic field (every voxel its own value, as the
     exactly integrated coefficients of Material.get_A_Ga are), so S1 streams it as a symmetric array."""
     n, ns, D = 255, 128, 3

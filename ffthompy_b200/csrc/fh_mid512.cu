@@ -10,7 +10,8 @@
 //   G^  on every (q, s), all D components                       2048 frequencies per tile
 //   I2, I1 the mirrored inverse.
 // Tile: 4 columns of all D components, [D][32][17][4] complex (one padding group per q: the radix-16 gathers of
-// 8 different q hit different banks), 209 KB for D = 6; 384 threads (D * 4 columns * 16), one CTA per SM.
+// 8 different q hit different banks), 209 KB for D = 6; 384 threads (D * 4 columns * 16), one CTA per SM.  (D = 3: 104 KB
+// and 192 threads; two CTAs per SM were measured and are SLOWER, 3.08 against 2.80 ms at 512^3 scalar, so one it stays.)
 // Addressing as in k_mid_green_reg3: natural [D][N][inner] or exchange buffers (rowoff / cstride), k2-blocks (kcol0),
 // optional scattered output rows (push exchange).  Reference semantics: ffthompy/projections.py:54-91,185-240 applied
 // between numpy.fft.fftn / ifftn along axis 0 (ffthompy/tensors/fft.py:39-43).

@@ -12,7 +12,7 @@ def timeit(fn, reps=10):
     for _ in range(reps): fn()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)/reps
-n = int(os.environ.get('BN', '256')); N = (n, n, n); D = int(os.environ.get('BD', '6'))
+n = int(os.environ.get('BN', '256')); N = tuple(int(os.environ.get('BN%d' % a, n)) for a in range(3)); D = int(os.environ.get('BD', '6'))
 p = C.c_void_p(); L.check(lib.fh_plan_create(C.byref(p), 3, L.i64arr(N)))
 x = torch.randn((D,)+N, dtype=torch.float64, device=dev); y = torch.zeros_like(x)
 mode = os.environ.get('BA', 'phase')
@@ -27,15 +27,15 @@ else:
     C1 = torch.eye(D, dtype=torch.float64, device=dev)*10+5
     A = (C0[:, :, None, None, None]*(1-ph)+C1[:, :, None, None, None]*ph).contiguous()
 g = L.fh_green(); g.kind = 1 if D == 6 else 0; g.dim = 3
-for a in range(3): g.N[a] = n; g.Y[a] = 1.0; g.band[a] = (n-((n+1) % 2)-1)//2
+for a in range(3): g.N[a] = N[a]; g.Y[a] = 1.0; g.band[a] = (N[a]-((N[a]+1) % 2)-1)//2
 g.cS, g.cH, g.scale = 1.0, -1.0, 1.0
 work = torch.zeros(lib.fh_ga_work_doubles(p, D), dtype=torch.float64, device=dev)
 op = C.c_void_p(); L.check(lib.fh_ga_create(C.byref(op), p, D, ptr(A), 0, C.byref(g), ptr(work)))
 fl, pi, mt = C.c_int(), C.c_int(), C.c_int(); L.check(lib.fh_ga_config(op, C.byref(fl), C.byref(pi), C.byref(mt)))
-nreal = n**3; F = 8*D*nreal; Fs = 16*D*n*n*pi.value; CA = 8*D*D*nreal
+nreal = N[0]*N[1]*N[2]; F = 8*D*nreal; Fs = 16*D*N[0]*N[1]*pi.value; CA = 8*D*D*nreal
 CA = {'rand': CA, 'sym': 8*(D*(D+1)//2)*nreal}.get(mode, nreal)
 alg = {1: F+CA+Fs, 2: 2*Fs, 3: 2*Fs, 4: 2*Fs, 5: Fs+2*F}
-out = ['A=%s cfg flags=%d pitch=%d midT=%d env=%s' % (mode, fl.value, pi.value, mt.value, {k: v for k, v in os.environ.items() if k.startswith('FH_')})]
+out = ['N=%s A=%s cfg flags=%d pitch=%d midT=%d env=%s' % (N, mode, fl.value, pi.value, mt.value, {k: v for k, v in os.environ.items() if k.startswith('FH_')})]
 for st in range(1, 6):
     t = timeit(lambda: L.check(lib.fh_ga_stage(op, st, ptr(x), ptr(y))))
     out.append('S%d %.3f ms %.0f GB/s' % (st, t, alg[st]/t/1e6))
