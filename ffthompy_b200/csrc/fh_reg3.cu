@@ -17,7 +17,11 @@ static int reg3_env(const char* name, int dflt) {
     const char* s = getenv(name);
     return s ? atoi(s) : dflt;
 }
-bool fh_reg3_last_len(int n) { return n == 512; }
+// 512 always; 1024 = 8 x 8 x 16 unless FH_REG3_1024=0 (then the generic shared-memory routine of fh_fast.cuh serves it)
+bool fh_reg3_last_len(int n) {
+    static const int l1024 = reg3_env("FH_REG3_1024", 1);
+    return n == 512 || (n == 1024 && l1024);
+}
 // axis-0 kernel: 512 always; 256 (8 columns per tile, 128-byte segments) when FH_MID256_REG3=1
 bool fh_reg3_mid_len(int n) {
     static const int m256 = reg3_env("FH_MID256_REG3", 0);
@@ -51,6 +55,9 @@ int fh_reg3_fwd_last(int N, int D, int trw, const Reg3LastArgs& a) {
     if (N == 512 && D == 6 && trw == 2) return fwd_last_D<512, 6, 2>(a);
     if (N == 512 && D == 3 && trw == 4) return fwd_last_D<512, 3, 4>(a);
     if (N == 512 && D == 2 && trw == 4) return fwd_last_D<512, 2, 4>(a);
+    if (N == 1024 && D == 6 && trw == 2) return fwd_last_D<1024, 6, 2>(a);
+    if (N == 1024 && D == 3 && trw == 4) return fwd_last_D<1024, 3, 4>(a);
+    if (N == 1024 && D == 2 && trw == 4) return fwd_last_D<1024, 2, 4>(a);
     return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass last-axis kernel for N=%d D=%d TRW=%d", N, D, trw);
 }
 
@@ -69,6 +76,9 @@ int fh_reg3_inv_last(int N, int D, int trw, const Reg3InvArgs& a) {
     if (N == 512 && D == 6 && trw == 2) return inv_last_D<512, 6, 2>(a);
     if (N == 512 && D == 3 && trw == 4) return inv_last_D<512, 3, 4>(a);
     if (N == 512 && D == 2 && trw == 4) return inv_last_D<512, 2, 4>(a);
+    if (N == 1024 && D == 6 && trw == 2) return inv_last_D<1024, 6, 2>(a);
+    if (N == 1024 && D == 3 && trw == 4) return inv_last_D<1024, 3, 4>(a);
+    if (N == 1024 && D == 2 && trw == 4) return inv_last_D<1024, 2, 4>(a);
     return fh_set_error(FH_ERR_UNSUPPORTED, "no three-pass last-axis kernel for N=%d D=%d TRW=%d", N, D, trw);
 }
 

@@ -39,17 +39,25 @@ __host__ __device__ __forceinline__ int reg3_freq_of_pos(int pos) {
 // the two lane orders of the pass-2 butterflies gives  p + p/16 + 2 (p/32) + 2 (p/64)  with q fastest in pass 2: every
 // access of the three passes and of phase 0 is conflict free, the separation costs 4 instead of 8 (24.5 wavefronts per
 // element and direction instead of 40; 20 is the floor).
+// 1024 = 8 x 8 x 16 (same search, 128 threads per line): p + p/16 + p/64 with q fastest in passes 2 AND 3 gives 22
+// wavefronts against 64 for p + p/8 (the separation alone costs 16 + 16 there).
 template <int N>
 struct LinePad {
     static constexpr int NPAD = N + N / 8;
-    static constexpr bool SWAP2 = false;
+    static constexpr bool SWAP2 = false, SWAP3 = false;
     static __host__ __device__ __forceinline__ int idx(int p) { return p + (p >> 3); }
 };
 template <>
 struct LinePad<512> {
     static constexpr int NPAD = 588;  // idx(511) = 586
-    static constexpr bool SWAP2 = true;
+    static constexpr bool SWAP2 = true, SWAP3 = false;
     static __host__ __device__ __forceinline__ int idx(int p) { return p + (p >> 4) + 2 * (p >> 5) + 2 * (p >> 6); }
+};
+template <>
+struct LinePad<1024> {
+    static constexpr int NPAD = 1104;  // idx(1023) = 1101
+    static constexpr bool SWAP2 = true, SWAP3 = true;
+    static __host__ __device__ __forceinline__ int idx(int p) { return p + (p >> 4) + (p >> 6); }
 };
 
 // ------------------------------------------------------------------ one line in SoA shared memory (last-axis kernels)
@@ -91,7 +99,7 @@ __device__ __forceinline__ void reg3_line_fwd(double* __restrict__ lre, double* 
     }
     __syncthreads();
     if (u < Reg3Cfg<N>::B3) {
-        const int q2 = u % R2, q = u / R2;  // q2 fastest: with pidx8 the runs of R3 start in distinct banks
+        const int q2 = LinePad<N>::SWAP3 ? u / R1 : u % R2, q = LinePad<N>::SWAP3 ? u % R1 : u / R2;  // lane order: LinePad
         const int b = q * M + q2 * R3;
         cplx v[R3];
 #pragma unroll
@@ -113,7 +121,7 @@ __device__ __forceinline__ void reg3_line_inv(double* __restrict__ lre, double* 
     constexpr int R1 = Reg3Cfg<N>::R1, R2 = Reg3Cfg<N>::R2, R3 = Reg3Cfg<N>::R3;
     constexpr int M = N / R1;
     if (u < Reg3Cfg<N>::B3) {
-        const int q2 = u % R2, q = u / R2;
+        const int q2 = LinePad<N>::SWAP3 ? u / R1 : u % R2, q = LinePad<N>::SWAP3 ? u % R1 : u / R2;
         const int b = q * M + q2 * R3;
         cplx v[R3];
 #pragma unroll
@@ -157,7 +165,7 @@ __device__ __forceinline__ void reg3_line_inv(double* __restrict__ lre, double* 
 // (three CTAs per SM: the CG form lives on the loads in flight; without the cap the 512 padding arithmetic takes the
 // kernel to 72 registers = two CTAs and S1 in its CG form loses 5 %)
 template <int N, int D, int TRW, int ALAY>
-__global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL, 3)
+__global__ void __launch_bounds__((D * TRW / 2) * Reg3Cfg<N>::TPL, ((D * TRW / 2) * Reg3Cfg<N>::TPL <= 384) ? 3 : 1)
     k_fwd_last_reg3(const double* __restrict__ A, const unsigned char* __restrict__ phase,
                     const double* __restrict__ lut, const Lut2C lutc, int nphase, double* __restrict__ p,
                     const double* __restrict__ r, const double* __restrict__ scal, int pupdate,

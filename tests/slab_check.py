@@ -32,7 +32,7 @@ def main():
     dev.init(local)
     ok = True
     for N in ([] if '--notest' in sys.argv else [(16, 16, 12), (64, 64, 64), (64, 128, 64), (32, 24, 20), (32, 16, 15), (128, 256, 32), (128, 16, 24), (256, 32, 16), (512, 16, 16),
-                                                     (16, 512, 16), (16, 16, 512)]):
+                                                     (16, 512, 16), (16, 16, 512), (16, 16, 1024)]):
         if N[0] % world or N[1] % world or (world > 2 and np.prod(N) > 300000):
             continue
         D = 6

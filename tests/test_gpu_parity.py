@@ -325,11 +325,11 @@ def test_full_size_properties(n):
         assert np.abs(Afun(u).val-ref).max() < 1e-12*np.abs(ref).max()
 
 
-@pytest.mark.parametrize('N', [(512, 8, 16), (8, 512, 16), (8, 16, 512), (512, 512)])
+@pytest.mark.parametrize('N', [(512, 8, 16), (8, 512, 16), (8, 16, 512), (512, 512), (8, 16, 1024), (6, 1024)])
 @pytest.mark.parametrize('physics', ['elasticity', 'scalar'])
 def test_axis_length_512_against_the_oracle(N, physics):
     """the register-resident three-pass kernels (csrc/fh_reg3.cuh: S1, S2/S4, S3, S5 at axis length 512, the
-    BASELINE config-4 grid size), one axis at a time: operator application vs the oracle 1e-12 relative, CG
+    BASELINE config-4 grid size; S1 / S5 also at 1024, the last axis of config 5), one axis at a time: operator application vs the oracle 1e-12 relative, CG
     iteration counts equal, solution 1e-9"""
     from ffthompy_b200.tensors import Tensor
     from ffthompy_b200.general.solver import linear_solver
