@@ -130,3 +130,26 @@ def test_install_splices_into_the_reference_tree():
         "print('spliced')\n") % (os.path.join(ROOT, 'oracle'), ROOT)
     out = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True)
     assert out.returncode == 0 and 'spliced' in out.stdout, out.stderr
+
+
+def test_line_padding_of_the_three_pass_kernels():
+    """`LinePad<512>` / `LinePad<1024>` (csrc/fh_reg3.cuh): the padded position is strictly increasing (so injective),
+    stays inside NPAD, and is what profiles/bank_conflict_search.py finds — 24.5 wavefronts per element and direction
+    against 40 for the round-1 padding p + p/8 (ncu measured that factor)."""
+    import importlib.util
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, 'ffthompy_b200', 'csrc', 'fh_reg3.cuh')).read()
+    npad = {int(n): int(v) for n, v in re.findall(r'struct LinePad<(\d+)> \{\s*static constexpr int NPAD = (\d+);', src)}
+    assert npad == {512: 588, 1024: 1104}
+    pads = {512: lambda p: p+(p >> 4)+2*(p >> 5)+2*(p >> 6), 1024: lambda p: p+(p >> 4)+(p >> 6)}
+    for n, pad in pads.items():
+        expr = re.search(r'struct LinePad<%d> \{.*?return (.*?); \}' % n, src, re.S).group(1)
+        assert eval(expr.replace('p', 'P'), {'P': 777 % n}) == pad(777 % n)       # the header holds the same formula
+        idx = [pad(p) for p in range(n)]
+        assert all(b > a for a, b in zip(idx, idx[1:])) and idx[-1] < npad[n]
+    spec = importlib.util.spec_from_file_location('bank_conflict_search', os.path.join(root, 'profiles', 'bank_conflict_search.py'))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    assert mod.score(lambda p: p+(p >> 3))[0] == 40.0
+    assert mod.score(pads[512])[0] == 24.5
