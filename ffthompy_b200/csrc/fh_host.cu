@@ -84,7 +84,15 @@ extern "C" int fh_download(void* dst, const void* src, int64_t bytes) {
         }
     };
     std::vector<std::thread> pool;
-    for (int t = 0; t < nthr; ++t) pool.emplace_back(worker);
+    try {
+        for (int t = 0; t < nthr; ++t) pool.emplace_back(worker);
+    } catch (...) {  // no threads to be had (restricted container): plain copy, ordered after the library stream
+        err.store(1);
+        for (auto& t : pool) t.join();
+        FH_CUDA(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, g_ring.stream));
+        FH_CUDA(cudaStreamSynchronize(g_ring.stream));
+        return FH_OK;
+    }
     cudaError_t ce = cudaSuccess;
     for (int64_t i = 0; i < nchunk && ce == cudaSuccess && !err.load(); ++i) {
         const int s = (int)(i % kSlots);
